@@ -1,0 +1,140 @@
+/* swinb200 -- C ABI of the B200 (sm_100a) kernels behind the SwinV2 weather-model training hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*), allocates
+ * nothing, never throws, and returns 0 on success or a SWINB200_ERR_* code (message available from
+ * swinb200_last_error()).  There are no torch types in this interface; the Python host code
+ * (swin_v2_weather_b200/ops.py) binds it with ctypes and passes tensor.data_ptr().
+ *
+ * Each function names the reference code it replaces (paths relative to NERSC/swin_v2_weather).
+ * "act" buffers hold activations in the compute mode's storage type: SWINB200_BF16 (training mode,
+ * tensor-core kernels) or SWINB200_F32 (fp32 validation mode, CUDA-core kernels).
+ * Layouts: tokens are row-major (B, H, W, C) == (T, C) with T = B*H*W; images are NCHW fp32.
+ */
+#ifndef SWINB200_H_
+#define SWINB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWINB200_VERSION 100
+
+enum { SWINB200_OK = 0, SWINB200_ERR_INVALID_ARG = 1, SWINB200_ERR_CUDA = 2, SWINB200_ERR_UNSUPPORTED = 3 };
+enum { SWINB200_F32 = 0, SWINB200_BF16 = 1 };
+
+/* GEMM epilogues (see swinb200_gemm) */
+enum {
+  SWINB200_EPI_BIAS = 0,      /* D = acc + bias                                 (D: act)             */
+  SWINB200_EPI_BIAS_GELU = 1, /* D2 = acc + bias ; D = gelu_erf(D2)             (D, D2: act)         */
+  SWINB200_EPI_DGELU = 2,     /* D = acc * gelu_erf'(aux)                       (D, aux: act)        */
+  SWINB200_EPI_ADD_F32 = 3,   /* D = acc + aux                                  (D, aux: fp32)       */
+  SWINB200_EPI_F32 = 4,       /* D = acc  (or D += acc when accumulate != 0)    (D: fp32)            */
+};
+/* GEMM back ends */
+enum { SWINB200_GEMM_SIMT = 0, SWINB200_GEMM_TCGEN05 = 1 };
+
+int swinb200_version(void);
+const char* swinb200_last_error(void);
+
+/* ---- parameter staging ------------------------------------------------------------------------
+ * fp32 master weights -> bf16 shadow used by the tensor-core GEMMs (no reference counterpart: the
+ * reference relies on torch autocast's per-call weight casts, train.py:277). */
+int swinb200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+
+/* ---- PatchEmbed / head data movement ------------------------------------------------------------
+ * swinb200_patchify: img (B, C, Hi, Wi) fp32 -> out (B*(Hi/P)*(Wi/P), C*P*P) act.
+ *   order 0: column k = (c*P + p)*P + q -- the Conv2d(k=s=P) im2col of PatchEmbed.proj
+ *            (swinv2_global.py:537,544; weight (E, C, P, P) flattened).
+ *   order 1: column k = (p*P + q)*C + c -- the inverse of forward_head's unpatchify
+ *            (swinv2_global.py:789-791); used on dL/dpred in backward.
+ * swinb200_unpatchify: y (T, P*P*Co) act, columns (p, q, c) -> out (B, Co, Hi, Wi) fp32,
+ *   out = unpatchify(y) + skip[:, :Co] (skip nullable; skip has skip_chans channels)
+ *   (swinv2_global.py:789-791, 795-802). */
+int swinb200_patchify(const float* img, void* out, int act_dtype, int B, int C, int Hi, int Wi, int P,
+                      int order, void* stream);
+int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out,
+                        int B, int Co, int Hi, int Wi, int P, void* stream);
+
+/* ---- GEMM ---------------------------------------------------------------------------------------
+ * D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ).
+ *   a_major 0: A stored (M, K) row-major, lda = row pitch;  1: A stored (K, M) row-major.
+ *   b_major 0: B stored (N, K) row-major (nn.Linear weight);  1: B stored (K, N) row-major.
+ * Replaces nn.Linear forward (a0,b0), its input gradient (a0,b1 with B = weight) and its weight
+ * gradient (a1,b1) -- swinv2_global.py:181,199,300,319,381-386,544,787 and their autograd
+ * backward.  in_dtype is the storage type of A and B.  split_k > 1 is allowed only with
+ * SWINB200_EPI_F32 and accumulate (atomic fp32 adds into a pre-initialised D).
+ * backend SWINB200_GEMM_TCGEN05 requires in_dtype == SWINB200_BF16. */
+int swinb200_gemm(int backend, int M, int N, int K, const void* A, int a_major, int lda, const void* B,
+                  int b_major, int ldb, int in_dtype, int epilogue, const float* bias, void* D, int ldd,
+                  void* D2, const void* aux, int ld_aux, int out_dtype, int accumulate, int split_k,
+                  void* stream);
+
+/* ---- LayerNorm + residual (post-norm) -------------------------------------------------------------
+ * fwd:  u = LN_C(z) * gamma + beta  (+ pos[t % rows_per_sample, c] if pos)  (* sample_scale[b] if given)
+ *       x_out = (x_in ? x_in : 0) + u ;  xb_out = act(x_out) ;  stats[row] = (mean, rstd)
+ *   == `x + drop_path(norm(branch))` (swinv2_global.py:490,494), and PatchEmbed.norm + pos_embed add
+ *   (swinv2_global.py:545,780) with x_in = NULL, pos = pos_embed transposed to token-major
+ *   (rows_per_sample, C) fp32 by swinb200_transpose_f32.
+ * bwd:  given dx = dL/dx_out (fp32): dz (act) ; dgamma, dbeta, dbias_prev += column sums (fp32 atomics,
+ *       caller zero-initialises).  dL/dx_in is dx itself (identity path), handled by the caller. */
+int swinb200_ln_residual_fwd(const void* z, int act_dtype, const float* x_in, const float* gamma,
+                             const float* beta, const float* sample_scale, const float* pos, float* x_out,
+                             void* xb_out, float* stats, int rows, int C, int rows_per_sample, float eps,
+                             void* stream);
+int swinb200_ln_residual_bwd(const float* dx, const void* z, int act_dtype, const float* stats,
+                             const float* gamma, const float* sample_scale, void* dz, float* dgamma,
+                             float* dbeta, float* dbias_prev, int rows, int C, int rows_per_sample,
+                             void* stream);
+/* dpos[c, t] = sum_b dx[b, t, c]  (gradient of the NCHW pos_embed parameter, swinv2_global.py:770,780) */
+int swinb200_pos_embed_grad(const float* dx, float* dpos, int B, int rows_per_sample, int C, void* stream);
+/* dst (Cc, R) = src (R, Cc)^T, fp32 (pos_embed NCHW <-> token-major staging) */
+int swinb200_transpose_f32(const float* src, float* dst, int R, int Cc, void* stream);
+
+/* out[col] += sum_rows x[row, col]  (bias gradients of nn.Linear) */
+int swinb200_colsum(const void* x, int act_dtype, float* out, int rows, int cols, int ld, void* stream);
+
+/* ---- windowed cosine attention ----------------------------------------------------------------------
+ * qk_normalize: in place on qkv (T, 3C): q and k of every (token, head) are divided by
+ *   max(||.||_2, 1e-12) (F.normalize, swinv2_global.py:185,304); inv_norm (T, 2, heads) fp32 receives
+ *   the reciprocal factors for backward.
+ * window_attn_fwd: per (sample, window, head), with roll(-s)/window_partition/window_reverse/roll(+s)
+ *   (swinv2_global.py:89-119,446-478) folded into addressing:
+ *     S = scale[h] * qhat khat^T (+ bias[h]) (+ shift mask) ; P = softmax(S) ; O = P v
+ *   (swinv2_global.py:185-198 / 304-318).  scale = exp(min(logit_scale, ln 100)) is passed in.
+ *   bias: nullable (heads, L, L) fp32 (continuous position bias table, :274-287).  The shift mask
+ *   ({0,-100}, :403-424) is generated in-kernel from (H, Wh, s0); swinb200_shift_mask materialises the
+ *   same predicate as the reference's (nW, L, L) buffer for bit-exact checks.
+ *   o: (T, C) act in un-rolled token order; lse: (B, nW, heads, L) fp32 log-sum-exp rows.
+ * window_attn_bwd: dqkv (T, 3C) act = gradients w.r.t. the *un-normalised* q, k and v;
+ *   dscale (heads) += sum dS * cos ; dbias (heads, L, L) += sum_windows dS (nullable).
+ * backend: SWINB200_GEMM_SIMT (CUDA cores, any act dtype) or SWINB200_GEMM_TCGEN05 (bf16). */
+int swinb200_qk_normalize(void* qkv, int act_dtype, float* inv_norm, int T, int C, int heads, void* stream);
+int swinb200_shift_mask(float* mask, int H, int W, int Wh, int Ww, int s0, int s1, void* stream);
+int swinb200_window_attn_fwd(int backend, const void* qkv, int act_dtype, const float* scale,
+                             const float* bias, void* o, float* lse, int B, int H, int W, int C, int heads,
+                             int Wh, int Ww, int s0, int s1, void* stream);
+int swinb200_window_attn_bwd(int backend, const void* qkv, int act_dtype, const float* inv_norm,
+                             const float* scale, const float* bias, const void* o, const void* d_o,
+                             const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W,
+                             int C, int heads, int Wh, int Ww, int s0, int s1, void* stream);
+
+/* ---- latitude-weighted L2 loss ------------------------------------------------------------------------
+ * fwd: num[b,c] = sum_hw qw[h] (p-t)^2 ; den[b,c] = sum_hw qw[h] t^2 ;
+ *      r = relative ? num/den : num ;  loss = sum_bc chw[c] * (squared ? r : sqrt(r))
+ *   == LossHandler -> GeometricLpLoss.rel/abs with p=2 (utils/losses.py:188-232,
+ *   utils/grids.py:115-117).  num/den/loss are fp32 outputs (B*C, B*C, 1); the entry point zeroes them.
+ * bwd: dprd = gloss * chw[c] * (squared ? 1 : 1/(2 sqrt(r))) * 2 qw[h] (p - t) / (relative ? den[b,c] : 1). */
+int swinb200_latw_l2_fwd(const float* prd, const float* tar, const float* qw, const float* chw, int relative,
+                         int squared, float* num, float* den, float* loss, int B, int C, int H, int W,
+                         void* stream);
+int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, const float* chw,
+                         const float* num, const float* den, const float* gloss, int relative, int squared,
+                         float* dprd, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWINB200_H_ */

@@ -1,0 +1,731 @@
+// Bandwidth-bound kernels of the SwinV2 hot path: parameter staging, patchify / unpatchify,
+// LayerNorm + residual (fwd/bwd), bias-gradient column sums, q/k L2-normalisation,
+// latitude-weighted L2 loss (fwd/bwd).  All accesses are 128-bit vectorised and coalesced;
+// reductions use warp shuffles first, shared memory second, fp32 atomics last.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace swinb200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  const size_t n8 = n / 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    ld8(src + i * 8, v);
+    st8(dst + i * 8, v);
+  }
+  if (blockIdx.x == 0) {
+    for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 2-D transpose (pos_embed (C, T) <-> (T, C)), optional sum over a leading batch of sources
+// ------------------------------------------------------------------------------------------------
+// dst[c, r] = sum_b src[b, r, c]   (src: (nb, R, Cc) ; dst: (Cc, R))
+__global__ void transpose_sum_kernel(const float* __restrict__ src, float* __restrict__ dst, int nb, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float acc = 0.f;
+    if (r < R && c < Cc)
+      for (int b = 0; b < nb; ++b) acc += src[((size_t)b * R + r) * Cc + c];
+    tile[j][tx] = acc;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < R && c < Cc) dst[(size_t)c * R + r] = tile[tx][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify / unpatchify
+// ------------------------------------------------------------------------------------------------
+constexpr int kPatchTok = 16;  // tokens per CTA
+
+// img (B, C, Hi, Wi) fp32 -> out (T, C*P*P).  P == 4 (float4 along the patch row).
+template <typename T, int ORDER>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int C,
+                                                       int Hi, int Wi, int ntok) {
+  constexpr int P = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int K = C * P * P;
+  const int pitch = K + 8;  // keeps rows 16-byte aligned, de-phases banks
+  const int H = Hi / P, W = Wi / P;
+  const int t0 = blockIdx.x * kPatchTok;
+  const int ntile = min(kPatchTok, ntok - t0);
+  // gather: one float4 (4 q-values) per (c, p, token)
+  const int items = C * P * kPatchTok;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int tok = it % kPatchTok;
+    const int cp = it / kPatchTok;
+    const int p = cp % P, c = cp / P;
+    if (tok >= ntile) continue;
+    const int t = t0 + tok;
+    const int j = t % W, i = (t / W) % H, b = t / (W * H);
+    const float4 v = *reinterpret_cast<const float4*>(img + (((size_t)b * C + c) * Hi + (i * P + p)) * Wi + j * P);
+    T* row = tile + (size_t)tok * pitch;
+    if (ORDER == 0) {
+      T* d = row + (c * P + p) * P;
+      Act<T>::st(d + 0, v.x); Act<T>::st(d + 1, v.y); Act<T>::st(d + 2, v.z); Act<T>::st(d + 3, v.w);
+    } else {
+      Act<T>::st(row + (p * P + 0) * C + c, v.x);
+      Act<T>::st(row + (p * P + 1) * C + c, v.y);
+      Act<T>::st(row + (p * P + 2) * C + c, v.z);
+      Act<T>::st(row + (p * P + 3) * C + c, v.w);
+    }
+  }
+  __syncthreads();
+  // contiguous store of ntile rows x K elements, 8 elements per thread-iteration
+  const int k8 = K / 8;
+  for (int it = threadIdx.x; it < ntile * k8; it += blockDim.x) {
+    const int tok = it / k8, kc = it % k8;
+    float v[8];
+    ld8(tile + (size_t)tok * pitch + kc * 8, v);
+    st8(out + (size_t)(t0 + tok) * K + kc * 8, v);
+  }
+}
+
+// y (T, P*P*Co) columns (p, q, c) -> out (B, Co, Hi, Wi) (+ skip[:, :Co])
+template <typename T>
+__global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y, const float* __restrict__ skip,
+                                                         int skip_chans, float* __restrict__ out, int B, int Co, int Hi,
+                                                         int Wi, int ntok) {
+  constexpr int P = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int K = Co * P * P;
+  const int pitch = K + 8;
+  const int H = Hi / P, W = Wi / P;
+  const int t0 = blockIdx.x * kPatchTok;
+  const int ntile = min(kPatchTok, ntok - t0);
+  const int k8 = K / 8;
+  for (int it = threadIdx.x; it < ntile * k8; it += blockDim.x) {
+    const int tok = it / k8, kc = it % k8;
+    float v[8];
+    ld8(y + (size_t)(t0 + tok) * K + kc * 8, v);
+    st8(tile + (size_t)tok * pitch + kc * 8, v);
+  }
+  __syncthreads();
+  const int items = Co * P * kPatchTok;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int tok = it % kPatchTok;
+    const int cp = it / kPatchTok;
+    const int p = cp % P, c = cp / P;
+    if (tok >= ntile) continue;
+    const int t = t0 + tok;
+    const int j = t % W, i = (t / W) % H, b = t / (W * H);
+    const T* row = tile + (size_t)tok * pitch;
+    float4 v;
+    v.x = Act<T>::ld(row + (p * P + 0) * Co + c);
+    v.y = Act<T>::ld(row + (p * P + 1) * Co + c);
+    v.z = Act<T>::ld(row + (p * P + 2) * Co + c);
+    v.w = Act<T>::ld(row + (p * P + 3) * Co + c);
+    const size_t pix = (size_t)(i * P + p) * Wi + j * P;
+    if (skip != nullptr) {
+      const float4 s = *reinterpret_cast<const float4*>(skip + ((size_t)b * skip_chans + c) * Hi * Wi + pix);
+      v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)b * Co + c) * Hi * Wi + pix) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + residual
+// ------------------------------------------------------------------------------------------------
+// One warp per row; lane owns chunks of 8 channels at c = lane*8 + 256*j.
+template <typename T, int NCHUNK>
+__global__ void __launch_bounds__(256) ln_residual_fwd_kernel(const T* __restrict__ z, const float* __restrict__ x_in,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ sample_scale,
+                                                              const float* __restrict__ pos, float* __restrict__ x_out,
+                                                              T* __restrict__ xb_out, float* __restrict__ stats, int rows,
+                                                              int C, int rows_per_sample, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * warps_per_block;
+  const float invC = 1.0f / (float)C;
+  for (int row = warp_global; row < rows; row += nwarps) {
+    float v[NCHUNK][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
+        ld8(z + (size_t)row * C + c, v[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[j][e];
+      }
+    }
+    const float mean = warp_sum(sum) * invC;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[j][e] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float var = warp_sum(sq) * invC;
+    const float rstd = rsqrtf(var + eps);
+    const float sc = sample_scale ? sample_scale[row / rows_per_sample] : 1.0f;
+    const int prow = row % rows_per_sample;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
+        float g[8], b[8], r[8];
+        ld8(gamma + c, g);
+        ld8(beta + c, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = (v[j][e] - mean) * rstd * g[e] + b[e];
+        if (pos) {
+          float pe[8];
+          ld8(pos + (size_t)prow * C + c, pe);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += pe[e];
+        }
+        if (sample_scale) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] *= sc;
+        }
+        if (x_in) {
+          float xi[8];
+          ld8(x_in + (size_t)row * C + c, xi);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += xi[e];
+        }
+        st8(x_out + (size_t)row * C + c, r);
+        st8(xb_out + (size_t)row * C + c, r);
+      }
+    }
+    if (lane == 0) {
+      stats[2 * (size_t)row] = mean;
+      stats[2 * (size_t)row + 1] = rstd;
+    }
+  }
+}
+
+// backward: dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dx*scale*gamma
+// column sums (dgamma, dbeta, dbias_prev) accumulated per lane across the warp's rows, reduced across
+// the block's warps in shared memory, then one fp32 atomic per column per block.
+template <typename T, int NCHUNK>
+__global__ void __launch_bounds__(256) ln_residual_bwd_kernel(const float* __restrict__ dx, const T* __restrict__ z,
+                                                              const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                              const float* __restrict__ sample_scale, T* __restrict__ dz,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ dbias_prev, int rows, int C,
+                                                              int rows_per_sample) {
+  extern __shared__ float red[];  // [3][C]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + wib;
+  const int nwarps = gridDim.x * warps_per_block;
+  const float invC = 1.0f / (float)C;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float a_g[NCHUNK][8], a_b[NCHUNK][8], a_z[NCHUNK][8];
+  float gm[NCHUNK][8];
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) {
+    const int c = lane * 8 + j * 256;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a_g[j][e] = 0.f; a_b[j][e] = 0.f; a_z[j][e] = 0.f; gm[j][e] = 0.f; }
+    if (c < C) ld8(gamma + c, gm[j]);
+  }
+  for (int row = warp_global; row < rows; row += nwarps) {
+    const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
+    const float sc = sample_scale ? sample_scale[row / rows_per_sample] : 1.0f;
+    float du[NCHUNK][8], xh[NCHUNK][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
+        float zz[8];
+        ld8(dx + (size_t)row * C + c, du[j]);
+        ld8(z + (size_t)row * C + c, zz);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          du[j][e] *= sc;
+          xh[j][e] = (zz[e] - mean) * rstd;
+          const float g = du[j][e] * gm[j][e];
+          s1 += g;
+          s2 += g * xh[j][e];
+          a_b[j][e] += du[j][e];
+          a_g[j][e] += du[j][e] * xh[j][e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = rstd * (du[j][e] * gm[j][e] - s1 - xh[j][e] * s2);
+          // the bias gradient of the preceding Linear sums what that Linear's backward will see,
+          // i.e. the stored (rounded) dz
+          a_z[j][e] += Act<T>::round(o[e]);
+        }
+        st8(dz + (size_t)row * C + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NCHUNK; ++j) {
+    const int c = lane * 8 + j * 256;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&red[c + e], a_g[j][e]);
+        atomicAdd(&red[C + c + e], a_b[j][e]);
+        atomicAdd(&red[2 * C + c + e], a_z[j][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[C + i]);
+    if (dbias_prev) atomicAdd(dbias_prev + i, red[2 * C + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int rows, int cols,
+                                                     int ld) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c < cols) {
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+      float v[8];
+      ld8(x + (size_t)r * ld + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ty][tx * 8 + e] = acc[e];
+  __syncthreads();
+  const int col = threadIdx.x;  // 256 columns per block
+  float s = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) s += red[y][col];
+  const int gc = blockIdx.x * 256 + col;
+  if (gc < cols) atomicAdd(out + gc, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k L2 normalisation (in place), LPV lanes per (token, head) vector
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) qk_normalize_kernel(T* __restrict__ qkv, float* __restrict__ inv_norm, int Tn, int C,
+                                                           int heads, int lpv, int cpl) {
+  const int d = C / heads;
+  const int nvec_per_tok = 2 * heads;
+  const size_t nvec = (size_t)Tn * nvec_per_tok;
+  const int groups_per_block = blockDim.x / lpv;
+  const int gl = threadIdx.x / lpv, li = threadIdx.x % lpv;
+  for (size_t g0 = (size_t)blockIdx.x * groups_per_block; g0 < nvec; g0 += (size_t)gridDim.x * groups_per_block) {
+    // every thread of the block runs the same trip count so the shuffles below stay warp-converged
+    const size_t g = g0 + gl;
+    const bool valid = g < nvec;
+    const size_t tok = valid ? g / nvec_per_tok : 0;
+    const int v = valid ? (int)(g % nvec_per_tok) : 0;
+    T* p = qkv + tok * 3 * (size_t)C + (size_t)v * d;
+    float x[6][8];
+    float ss = 0.f;
+    for (int j = 0; j < cpl; ++j) {
+      if (valid) {
+        ld8(p + (li + j * lpv) * 8, x[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += x[j][e] * x[j][e];
+      }
+    }
+    for (int o = lpv >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (valid) {
+      for (int j = 0; j < cpl; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[j][e] *= inv;
+        st8(p + (li + j * lpv) * 8, x[j]);
+      }
+      if (li == 0) inv_norm[g] = inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shifted-window mask, materialised as the reference's (nW, L, L) buffer
+// ------------------------------------------------------------------------------------------------
+__global__ void shift_mask_kernel(float* __restrict__ mask, int H, int W, int Wh, int Ww, int s0) {
+  const int L = Wh * Ww;
+  const int nWw = W / Ww;
+  const size_t total = (size_t)(H / Wh) * nWw * L * L;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i % L);
+    const int n = (int)((i / L) % L);
+    const int w = (int)(i / ((size_t)L * L));
+    const int wh = w / nWw;
+    const int ln = shift_region_label(wh * Wh + n / Ww, H, s0);
+    const int lm = shift_region_label(wh * Wh + m / Ww, H, s0);
+    mask[i] = (ln != lm) ? -100.0f : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// latitude-weighted L2 loss
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) latw_l2_fwd_kernel(const float* __restrict__ prd, const float* __restrict__ tar,
+                                                          const float* __restrict__ qw, float* __restrict__ num,
+                                                          float* __restrict__ den, int H, int W, int rows_per_block) {
+  __shared__ float rn[8], rd[8];
+  const int plane = blockIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(H, r0 + rows_per_block);
+  const int w4 = W / 4;
+  const float4* p4 = reinterpret_cast<const float4*>(prd + (size_t)plane * H * W);
+  const float4* t4 = reinterpret_cast<const float4*>(tar + (size_t)plane * H * W);
+  float an = 0.f, ad = 0.f;
+  const int n4 = (r1 - r0) * w4;
+  const size_t base = (size_t)r0 * w4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x * 4) {
+    float4 p[4], t[4];
+    float q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ii = i + u * blockDim.x;
+      if (ii < n4) {
+        p[u] = __ldg(p4 + base + ii);
+        t[u] = __ldg(t4 + base + ii);
+        q[u] = __ldg(qw + r0 + ii / w4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ii = i + u * blockDim.x;
+      if (ii < n4) {
+        const float dx = p[u].x - t[u].x, dy = p[u].y - t[u].y, dz = p[u].z - t[u].z, dw = p[u].w - t[u].w;
+        an += q[u] * ((dx * dx + dy * dy) + (dz * dz + dw * dw));
+        ad += q[u] * ((t[u].x * t[u].x + t[u].y * t[u].y) + (t[u].z * t[u].z + t[u].w * t[u].w));
+      }
+    }
+  }
+  an = warp_sum(an);
+  ad = warp_sum(ad);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { rn[wid] = an; rd[wid] = ad; }
+  __syncthreads();
+  if (wid == 0) {
+    an = lane < (int)(blockDim.x >> 5) ? rn[lane] : 0.f;
+    ad = lane < (int)(blockDim.x >> 5) ? rd[lane] : 0.f;
+    an = warp_sum(an);
+    ad = warp_sum(ad);
+    if (lane == 0) {
+      atomicAdd(num + plane, an);
+      atomicAdd(den + plane, ad);
+    }
+  }
+}
+
+__global__ void latw_l2_finish_kernel(const float* __restrict__ num, const float* __restrict__ den,
+                                      const float* __restrict__ chw, int relative, int squared,
+                                      float* __restrict__ loss, int BC, int C) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < BC; i += blockDim.x) {
+    float v = relative ? num[i] / den[i] : num[i];
+    if (!squared) v = sqrtf(v);
+    acc += chw[i % C] * v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) *loss = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) latw_l2_bwd_kernel(const float* __restrict__ prd, const float* __restrict__ tar,
+                                                          const float* __restrict__ qw, const float* __restrict__ chw,
+                                                          const float* __restrict__ num, const float* __restrict__ den,
+                                                          const float* __restrict__ gloss, int relative, int squared,
+                                                          float* __restrict__ dprd, int C, int H, int W, int rows_per_block) {
+  const int plane = blockIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(H, r0 + rows_per_block);
+  const int w4 = W / 4;
+  float coef = 2.0f * gloss[0] * chw[plane % C] / (relative ? den[plane] : 1.0f);
+  if (!squared) coef *= 0.5f * rsqrtf(relative ? num[plane] / den[plane] : num[plane]);
+  const float4* p4 = reinterpret_cast<const float4*>(prd + (size_t)plane * H * W);
+  const float4* t4 = reinterpret_cast<const float4*>(tar + (size_t)plane * H * W);
+  float4* d4 = reinterpret_cast<float4*>(dprd + (size_t)plane * H * W);
+  const int n4 = (r1 - r0) * w4;
+  const size_t base = (size_t)r0 * w4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 p = __ldg(p4 + base + i), t = __ldg(t4 + base + i);
+    const float s = coef * __ldg(qw + r0 + i / w4);
+    d4[base + i] = make_float4(s * (p.x - t.x), s * (p.y - t.y), s * (p.z - t.z), s * (p.w - t.w));
+  }
+}
+
+}  // namespace swinb200
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace swinb200;
+
+extern "C" int swinb200_version(void) { return SWINB200_VERSION; }
+extern "C" const char* swinb200_last_error(void) { return g_err; }
+
+extern "C" int swinb200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  SWB_CHECK_ARG(src && dst, "cast: null pointer");
+  SWB_CHECK_ARG(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "cast: pointers must be 16-byte aligned");
+  if (n == 0) return SWINB200_OK;
+  const int blocks = (int)min((size_t)sm_count() * 8, (n / 8 + 255) / 256 + 1);
+  cast_f32_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_pos_embed_grad(const float* dx, float* dpos, int B, int rows_per_sample, int C, void* stream) {
+  SWB_CHECK_ARG(dx && dpos && B > 0 && rows_per_sample > 0 && C > 0, "pos_embed_grad: bad arguments");
+  dim3 grid((rows_per_sample + 31) / 32, (C + 31) / 32), block(32, 8);
+  transpose_sum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dx, dpos, B, rows_per_sample, C);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_transpose_f32(const float* src, float* dst, int R, int Cc, void* stream) {
+  // dst (Cc, R) = src (R, Cc)^T
+  return swinb200_pos_embed_grad(src, dst, 1, R, Cc, stream);
+}
+
+template <typename T>
+static int launch_patchify(const float* img, T* out, int B, int C, int Hi, int Wi, int order, cudaStream_t s) {
+  const int ntok = B * (Hi / 4) * (Wi / 4);
+  const int K = C * 16;
+  const size_t smem = (size_t)kPatchTok * (K + 8) * sizeof(T);
+  const int blocks = (ntok + kPatchTok - 1) / kPatchTok;
+  if (order == 0) {
+    SWB_CUDA(cudaFuncSetAttribute(patchify_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patchify_kernel<T, 0><<<blocks, 256, smem, s>>>(img, out, B, C, Hi, Wi, ntok);
+  } else {
+    SWB_CUDA(cudaFuncSetAttribute(patchify_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patchify_kernel<T, 1><<<blocks, 256, smem, s>>>(img, out, B, C, Hi, Wi, ntok);
+  }
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_patchify(const float* img, void* out, int act_dtype, int B, int C, int Hi, int Wi, int P, int order,
+                                 void* stream) {
+  SWB_CHECK_ARG(img && out, "patchify: null pointer");
+  SWB_CHECK_ARG(P == 4, "patchify: only patch_size 4 is supported (got %d)", P);
+  SWB_CHECK_ARG(B > 0 && C > 0 && Hi % 4 == 0 && Wi % 4 == 0, "patchify: bad shape B=%d C=%d Hi=%d Wi=%d", B, C, Hi, Wi);
+  SWB_CHECK_ARG((C * 16) % 8 == 0 && (size_t)kPatchTok * (C * 16 + 8) * 4 <= 220 * 1024, "patchify: C=%d too large", C);
+  SWB_CHECK_ARG(order == 0 || order == 1, "patchify: order must be 0 or 1");
+  if (act_dtype == SWINB200_BF16) return launch_patchify<__nv_bfloat16>(img, (__nv_bfloat16*)out, B, C, Hi, Wi, order, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32) return launch_patchify<float>(img, (float*)out, B, C, Hi, Wi, order, (cudaStream_t)stream);
+  SWB_CHECK_ARG(false, "patchify: bad act_dtype %d", act_dtype);
+}
+
+template <typename T>
+static int launch_unpatchify(const T* y, const float* skip, int skip_chans, float* out, int B, int Co, int Hi, int Wi,
+                             cudaStream_t s) {
+  const int ntok = B * (Hi / 4) * (Wi / 4);
+  const int K = Co * 16;
+  const size_t smem = (size_t)kPatchTok * (K + 8) * sizeof(T);
+  SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unpatchify_kernel<T><<<(ntok + kPatchTok - 1) / kPatchTok, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out, int B, int Co,
+                                   int Hi, int Wi, int P, void* stream) {
+  SWB_CHECK_ARG(y && out, "unpatchify: null pointer");
+  SWB_CHECK_ARG(P == 4, "unpatchify: only patch_size 4 is supported (got %d)", P);
+  SWB_CHECK_ARG(B > 0 && Co > 0 && Hi % 4 == 0 && Wi % 4 == 0, "unpatchify: bad shape");
+  SWB_CHECK_ARG(skip == nullptr || skip_chans >= Co, "unpatchify: skip has fewer channels (%d) than the output (%d)", skip_chans, Co);
+  SWB_CHECK_ARG((size_t)kPatchTok * (Co * 16 + 8) * 4 <= 220 * 1024, "unpatchify: Co=%d too large", Co);
+  if (act_dtype == SWINB200_BF16) return launch_unpatchify<__nv_bfloat16>((const __nv_bfloat16*)y, skip, skip_chans, out, B, Co, Hi, Wi, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32) return launch_unpatchify<float>((const float*)y, skip, skip_chans, out, B, Co, Hi, Wi, (cudaStream_t)stream);
+  SWB_CHECK_ARG(false, "unpatchify: bad act_dtype %d", act_dtype);
+}
+
+template <typename T>
+static int launch_ln_fwd(const T* z, const float* x_in, const float* gamma, const float* beta, const float* ss,
+                         const float* pos, float* x_out, T* xb, float* stats, int rows, int C, int rps, float eps,
+                         cudaStream_t s) {
+  const int blocks = min((rows + 7) / 8, sm_count() * 8);
+  const int nchunk = (C + 255) / 256;
+#define SWB_LN_FWD(N) ln_residual_fwd_kernel<T, N><<<blocks, 256, 0, s>>>(z, x_in, gamma, beta, ss, pos, x_out, xb, stats, rows, C, rps, eps)
+  switch (nchunk) {
+    case 1: SWB_LN_FWD(1); break;
+    case 2: SWB_LN_FWD(2); break;
+    case 3: SWB_LN_FWD(3); break;
+    case 4: SWB_LN_FWD(4); break;
+    default: set_error("ln_residual_fwd: C=%d > 1024 unsupported", C); return SWINB200_ERR_UNSUPPORTED;
+  }
+#undef SWB_LN_FWD
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_ln_residual_fwd(const void* z, int act_dtype, const float* x_in, const float* gamma, const float* beta,
+                                        const float* sample_scale, const float* pos, float* x_out, void* xb_out, float* stats,
+                                        int rows, int C, int rows_per_sample, float eps, void* stream) {
+  SWB_CHECK_ARG(z && gamma && beta && x_out && xb_out && stats, "ln_residual_fwd: null pointer");
+  SWB_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && rows_per_sample > 0, "ln_residual_fwd: bad shape rows=%d C=%d", rows, C);
+  if (act_dtype == SWINB200_BF16)
+    return launch_ln_fwd<__nv_bfloat16>((const __nv_bfloat16*)z, x_in, gamma, beta, sample_scale, pos, x_out, (__nv_bfloat16*)xb_out, stats, rows, C, rows_per_sample, eps, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32)
+    return launch_ln_fwd<float>((const float*)z, x_in, gamma, beta, sample_scale, pos, x_out, (float*)xb_out, stats, rows, C, rows_per_sample, eps, (cudaStream_t)stream);
+  SWB_CHECK_ARG(false, "ln_residual_fwd: bad act_dtype %d", act_dtype);
+}
+
+template <typename T>
+static int launch_ln_bwd(const float* dx, const T* z, const float* stats, const float* gamma, const float* ss, T* dz,
+                         float* dgamma, float* dbeta, float* dbias_prev, int rows, int C, int rps, cudaStream_t s) {
+  const int blocks = min((rows + 7) / 8, sm_count() * 2);
+  const int nchunk = (C + 255) / 256;
+  const size_t smem = 3 * (size_t)C * sizeof(float);
+#define SWB_LN_BWD(N) ln_residual_bwd_kernel<T, N><<<blocks, 256, smem, s>>>(dx, z, stats, gamma, ss, dz, dgamma, dbeta, dbias_prev, rows, C, rps)
+  switch (nchunk) {
+    case 1: SWB_LN_BWD(1); break;
+    case 2: SWB_LN_BWD(2); break;
+    case 3: SWB_LN_BWD(3); break;
+    case 4: SWB_LN_BWD(4); break;
+    default: set_error("ln_residual_bwd: C=%d > 1024 unsupported", C); return SWINB200_ERR_UNSUPPORTED;
+  }
+#undef SWB_LN_BWD
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_ln_residual_bwd(const float* dx, const void* z, int act_dtype, const float* stats, const float* gamma,
+                                        const float* sample_scale, void* dz, float* dgamma, float* dbeta, float* dbias_prev,
+                                        int rows, int C, int rows_per_sample, void* stream) {
+  SWB_CHECK_ARG(dx && z && stats && gamma && dz && dgamma && dbeta, "ln_residual_bwd: null pointer");
+  SWB_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && rows_per_sample > 0, "ln_residual_bwd: bad shape rows=%d C=%d", rows, C);
+  if (act_dtype == SWINB200_BF16)
+    return launch_ln_bwd<__nv_bfloat16>(dx, (const __nv_bfloat16*)z, stats, gamma, sample_scale, (__nv_bfloat16*)dz, dgamma, dbeta, dbias_prev, rows, C, rows_per_sample, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32)
+    return launch_ln_bwd<float>(dx, (const float*)z, stats, gamma, sample_scale, (float*)dz, dgamma, dbeta, dbias_prev, rows, C, rows_per_sample, (cudaStream_t)stream);
+  SWB_CHECK_ARG(false, "ln_residual_bwd: bad act_dtype %d", act_dtype);
+}
+
+extern "C" int swinb200_colsum(const void* x, int act_dtype, float* out, int rows, int cols, int ld, void* stream) {
+  SWB_CHECK_ARG(x && out && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, "colsum: bad arguments rows=%d cols=%d ld=%d", rows, cols, ld);
+  const int gx = (cols + 255) / 256;
+  int gy = max(1, min((rows + 63) / 64, (sm_count() * 4 + gx - 1) / gx));
+  dim3 grid(gx, gy);
+  if (act_dtype == SWINB200_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, cols, ld);
+  else if (act_dtype == SWINB200_F32)
+    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, out, rows, cols, ld);
+  else
+    SWB_CHECK_ARG(false, "colsum: bad act_dtype %d", act_dtype);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_qk_normalize(void* qkv, int act_dtype, float* inv_norm, int T, int C, int heads, void* stream) {
+  SWB_CHECK_ARG(qkv && inv_norm && T > 0 && heads > 0 && C % heads == 0, "qk_normalize: bad arguments");
+  const int d = C / heads;
+  SWB_CHECK_ARG(d % 8 == 0, "qk_normalize: head_dim %d must be a multiple of 8", d);
+  const int chunks = d / 8;
+  int lpv = 1;
+  while (lpv < 8 && chunks % (lpv * 2) == 0) lpv *= 2;
+  const int cpl = chunks / lpv;
+  SWB_CHECK_ARG(cpl <= 6, "qk_normalize: head_dim %d unsupported (chunks per lane %d > 6)", d, cpl);
+  const size_t nvec = (size_t)T * 2 * heads;
+  const int gpb = 256 / lpv;
+  const int blocks = (int)min((nvec + gpb - 1) / gpb, (size_t)sm_count() * 16);
+  if (act_dtype == SWINB200_BF16)
+    qk_normalize_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv, inv_norm, T, C, heads, lpv, cpl);
+  else if (act_dtype == SWINB200_F32)
+    qk_normalize_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)qkv, inv_norm, T, C, heads, lpv, cpl);
+  else
+    SWB_CHECK_ARG(false, "qk_normalize: bad act_dtype %d", act_dtype);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_shift_mask(float* mask, int H, int W, int Wh, int Ww, int s0, int s1, void* stream) {
+  SWB_CHECK_ARG(mask && H > 0 && W > 0 && Wh > 0 && Ww > 0 && H % Wh == 0 && W % Ww == 0, "shift_mask: bad geometry");
+  SWB_CHECK_ARG(s0 > 0 || s1 > 0, "shift_mask: un-shifted blocks have no mask");
+  shift_mask_kernel<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(mask, H, W, Wh, Ww, s0);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_latw_l2_fwd(const float* prd, const float* tar, const float* qw, const float* chw, int relative,
+                                    int squared, float* num, float* den, float* loss, int B, int C, int H, int W,
+                                    void* stream) {
+  SWB_CHECK_ARG(prd && tar && qw && chw && num && den && loss, "latw_l2_fwd: null pointer");
+  SWB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "latw_l2_fwd: bad shape (W must be a multiple of 4)");
+  cudaStream_t s = (cudaStream_t)stream;
+  SWB_CUDA(cudaMemsetAsync(num, 0, sizeof(float) * B * C, s));
+  SWB_CUDA(cudaMemsetAsync(den, 0, sizeof(float) * B * C, s));
+  const int planes = B * C;
+  int split = max(1, (sm_count() * 8 + planes - 1) / planes);
+  int rpb = max(1, (H + split - 1) / split);
+  split = (H + rpb - 1) / rpb;
+  latw_l2_fwd_kernel<<<dim3(planes, split), 256, 0, s>>>(prd, tar, qw, num, den, H, W, rpb);
+  SWB_LAUNCH_CHECK();
+  latw_l2_finish_kernel<<<1, 256, 0, s>>>(num, den, chw, relative, squared, loss, planes, C);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+extern "C" int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, const float* chw, const float* num,
+                                    const float* den, const float* gloss, int relative, int squared, float* dprd, int B, int C,
+                                    int H, int W, void* stream) {
+  SWB_CHECK_ARG(prd && tar && qw && chw && gloss && dprd && (den || !relative) && (num || squared), "latw_l2_bwd: null pointer");
+  SWB_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "latw_l2_bwd: bad shape");
+  const int planes = B * C;
+  int split = max(1, (sm_count() * 8 + planes - 1) / planes);
+  int rpb = max(1, (H + split - 1) / split);
+  split = (H + rpb - 1) / rpb;
+  latw_l2_bwd_kernel<<<dim3(planes, split), 256, 0, (cudaStream_t)stream>>>(prd, tar, qw, chw, num, den, gloss, relative, squared, dprd, C, H, W, rpb);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}

@@ -1,0 +1,379 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one thread: tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores)
+// Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
+// so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
+// token-major, reduction over tokens, optional split-K with fp32 red.global) all run without transposed copies.
+#include <cuda.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace swinb200 {
+
+using namespace ptx;
+
+constexpr int GBM = 128;  // UMMA M (cta_group::1)
+constexpr int GBK = 64;   // k per pipeline stage (one 128-byte swizzle row of bf16)
+constexpr int kGemmThreads = 192;
+
+struct GemmTcParams {
+  int M, N, K;
+  const float* bias;
+  void* D;
+  void* D2;
+  const void* aux;
+  int ldd, ld_aux;
+  int atomic_out;  // EPI_F32: 1 = red.global.add (split-K / accumulate), 0 = plain store
+  int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = GBM * GBK * 2;
+  static constexpr int kStageB = BN * GBK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =============================== TMA producer ===============================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile % p.split_k;
+        const int rest = tile / p.split_k;
+        const int n0 = (rest % p.num_n_tiles) * BN;
+        const int m0 = (rest / p.num_n_tiles) * GBM;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          unsigned char* sa = smem + stage * Cfg::kStage;
+          unsigned char* sb = sa + Cfg::kStageA;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          const int k0 = kb * GBK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < GBM / 64; ++c)  // box {64 m, 64 k}
+              tma_load_2d(sa + c * (64 * GBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)  // box {64 n, 64 k}
+              tma_load_2d(sb + c * (64 * GBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // =============================== MMA issuer =================================
+      constexpr uint32_t idesc = umma_idesc_bf16(GBM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart, k advances 32 B inside the swizzle row.
+      // MN-major: 8-k groups 1024 B apart, 64-wide m/n chunks 64*128 B apart, k advances 16 rows = 2048 B.
+      constexpr uint32_t kLboMn = 64 * GBK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int ks = tile % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int buf = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1, 200 + buf);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t sb = sa + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < GBK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sa + k * 2048, kLboMn, 1024)
+                                        : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, kLboMn, 1024)
+                                        : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================================= epilogue ===================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int rest = tile / p.split_k;
+      const int n0 = (rest % p.num_n_tiles) * BN;
+      const int m0 = (rest / p.num_n_tiles) * GBM;
+      const int buf = local & 1;
+      const uint32_t use = (uint32_t)(local >> 1);
+      mbar_wait(&tfull_bar[buf], use & 1, 400 + buf);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + cc * 32), r);
+        tmem_ld_wait();
+        const int nb = n0 + cc * 32;
+        if (row_ok && nb < p.N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU) {
+            if (p.bias) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (nb + g * 4 < p.N) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
+                  v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+                }
+              }
+            }
+          }
+          if (EPI == SWINB200_EPI_BIAS) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (nb + g * 8 < p.N) {
+                float t8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t8[e] = v[g * 8 + e];
+                st8(d + g * 8, t8);
+              }
+          } else if (EPI == SWINB200_EPI_BIAS_GELU) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
+            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + nb;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (nb + g * 8 < p.N) {
+                float h8[8], g8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  h8[e] = v[g * 8 + e];
+                  g8[e] = gelu_erf(Act<__nv_bfloat16>::round(h8[e]));
+                }
+                st8(d2 + g * 8, h8);
+                st8(d + g * 8, g8);
+              }
+          } else if (EPI == SWINB200_EPI_DGELU) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
+            const __nv_bfloat16* hx = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + nb;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (nb + g * 8 < p.N) {
+                float h8[8], o8[8];
+                ld8(hx + g * 8, h8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o8[e] = v[g * 8 + e] * gelu_erf_grad(h8[e]);
+                st8(d + g * 8, o8);
+              }
+          } else if (EPI == SWINB200_EPI_ADD_F32) {
+            float* d = reinterpret_cast<float*>(p.D) + (size_t)m * p.ldd + nb;
+            const float* ax = reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + nb;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (nb + g * 4 < p.N) {
+                const float4 a4 = *reinterpret_cast<const float4*>(ax + g * 4);
+                *reinterpret_cast<float4*>(d + g * 4) =
+                    make_float4(v[g * 4] + a4.x, v[g * 4 + 1] + a4.y, v[g * 4 + 2] + a4.z, v[g * 4 + 3] + a4.w);
+              }
+          } else {  // EPI_F32
+            float* d = reinterpret_cast<float*>(p.D) + (size_t)m * p.ldd + nb;
+            if (p.atomic_out) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (nb + g * 4 < p.N)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + g * 4), "f"(v[g * 4]),
+                               "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
+                               : "memory");
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (nb + g * 4 < p.N)
+                  *reinterpret_cast<float4*>(d + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle
+int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SWINB200_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return SWINB200_ERR_CUDA;
+  }
+  return SWINB200_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    SWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int grid = min(tiles, sm_count());
+  kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, p);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+// Only the operand-major / epilogue pairs the model uses are instantiated:
+//   forward  (A k-major, B k-major) : BIAS, BIAS_GELU, F32
+//   dgrad    (A k-major, B n-major) : BIAS (no bias pointer), DGELU, ADD_F32, F32
+//   wgrad    (A m-major, B n-major) : F32 (plain or split-K atomic)
+template <int BN>
+static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p,
+                    cudaStream_t s) {
+  if (!a_major && !b_major) {
+    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, false, SWINB200_EPI_BIAS>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_BIAS_GELU) return launch_tc<BN, false, false, SWINB200_EPI_BIAS_GELU>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, false, SWINB200_EPI_F32>(tmA, tmB, p, s);
+  } else if (!a_major && b_major) {
+    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, true, SWINB200_EPI_BIAS>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_DGELU) return launch_tc<BN, false, true, SWINB200_EPI_DGELU>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_ADD_F32) return launch_tc<BN, false, true, SWINB200_EPI_ADD_F32>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, true, SWINB200_EPI_F32>(tmA, tmB, p, s);
+  } else if (a_major && b_major) {
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, true, true, SWINB200_EPI_F32>(tmA, tmB, p, s);
+  }
+  set_error("gemm(tcgen05): combination a_major=%d b_major=%d epilogue=%d is not instantiated", a_major, b_major, epi);
+  return SWINB200_ERR_UNSUPPORTED;
+}
+
+int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
+                 const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
+                 cudaStream_t stream) {
+  SWB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm(tcgen05): lda/ldb must be multiples of 8 elements (16 bytes)");
+  SWB_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "gemm(tcgen05): N and ldd must be multiples of 8");
+  SWB_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0), "gemm(tcgen05): operands must be 16-byte aligned");
+  SWB_CHECK_ARG(aux == nullptr || (((uintptr_t)aux % 16 == 0) && ld_aux % 8 == 0), "gemm(tcgen05): aux must be 16-byte aligned with ld_aux %% 8 == 0");
+  SWB_CHECK_ARG(D2 == nullptr || ((uintptr_t)D2 % 16 == 0), "gemm(tcgen05): D2 must be 16-byte aligned");
+  SWB_CHECK_ARG(bias == nullptr || ((uintptr_t)bias % 16 == 0), "gemm(tcgen05): bias must be 16-byte aligned");
+
+  const int BN = (N > 128) ? 256 : 128;
+  GemmTcParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.D = D; p.D2 = D2; p.aux = aux; p.ldd = ldd; p.ld_aux = ld_aux;
+  p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
+  p.num_m_tiles = (M + GBM - 1) / GBM;
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.kb_total = (K + GBK - 1) / GBK;
+  split_k = max(1, min(split_k, p.kb_total));
+  p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+
+  CUtensorMap tmA, tmB;
+  int e;
+  if (!a_major) e = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GBK, GBM);
+  else e = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GBK);
+  if (e) return e;
+  if (!b_major) e = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)BN);
+  else e = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
+  if (e) return e;
+
+  if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, p, stream);
+  return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, p, stream);
+}
+
+}  // namespace swinb200

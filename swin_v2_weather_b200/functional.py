@@ -1,0 +1,217 @@
+"""Autograd wiring of the hot path: each Function's forward/backward is a fixed sequence of our CUDA
+kernels (swin_v2_weather_b200/ops.py).  Nothing here computes with PyTorch ops except trivial views.
+
+Saved-for-backward per block (bf16 mode, per token): xb, qkv (q^,k^,v), o, z1, xb_mid, h, g, z2 in
+activation storage + fp32 row statistics -- ~24.6 KB/token, 1.6 GB per block per 64,800-token sample.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import ComputeMode, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_F32
+
+
+# ---- bf16 weight shadows ------------------------------------------------------------------------------
+class _ShadowCache:
+    """bf16 copies of fp32 master weights, refreshed when the parameter's version counter moves
+    (optimizer.step() bumps it).  Parameters themselves are never replaced (optimizer / DDP hold them)."""
+
+    def __init__(self):
+        self._store: Dict[int, Tuple[int, int, torch.Tensor]] = {}
+
+    def get(self, w: torch.Tensor, mode: ComputeMode) -> torch.Tensor:
+        if mode.act_dtype == torch.float32:
+            return w.detach()
+        key = id(w)
+        ent = self._store.get(key)
+        ver, ptr = w._version, w.data_ptr()
+        if ent is not None and ent[0] == ver and ent[1] == ptr:
+            return ent[2]
+        out = ent[2] if (ent is not None and ent[2].shape == w.shape and ent[2].device == w.device) else None
+        sh = ops.cast_bf16(w.detach().contiguous(), out)
+        self._store[key] = (ver, ptr, sh)
+        return sh
+
+    def clear(self):
+        self._store.clear()
+
+
+SHADOWS = _ShadowCache()
+
+
+def _flat2(w: torch.Tensor) -> torch.Tensor:
+    return w.reshape(w.shape[0], -1)
+
+
+# ---- PatchEmbed (+ LayerNorm + pos_embed) --------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """reference: PatchEmbed.forward + `x + pos_embed` (swinv2_global.py:540-546, 779-780).
+    Returns the fp32 token stream (B, H, W, C) and its activation-type shadow."""
+
+    @staticmethod
+    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode):
+        B, Cin, Hi, Wi = img.shape
+        E = proj_w.shape[0]
+        H, W = Hi // patch, Wi // patch
+        patches = ops.patchify(img.contiguous(), patch, 0, mode)                       # (T, Cin*P*P)
+        w2 = SHADOWS.get(proj_w, mode).reshape(E, -1)
+        z0 = ops.gemm(mode, patches, 0, w2, 0, EPI_BIAS, bias=proj_b.detach())        # (T, E)
+        pos_tok = None
+        if pos_embed is not None:
+            pos_tok = ops.transpose_f32(pos_embed.detach().reshape(E, H * W))          # (H*W, E) token-major
+        x, xb, stats = ops.ln_residual_fwd(z0, None, norm_w.detach(), norm_b.detach(), None, pos_tok, H * W, mode)
+        ctx.save_for_backward(patches, z0, stats, norm_w)
+        ctx.meta = (B, Cin, Hi, Wi, E, H, W, patch, mode, pos_embed is not None, tuple(proj_w.shape))
+        shadow = xb if mode.act_dtype != torch.float32 else x.new_empty(0)   # fp32 mode: the stream is its own shadow
+        ctx.mark_non_differentiable(shadow)
+        return x.view(B, H, W, E), shadow
+
+    @staticmethod
+    def backward(ctx, dx, _dxb):
+        patches, z0, stats, norm_w = ctx.saved_tensors
+        B, Cin, Hi, Wi, E, H, W, patch, mode, has_pos, wshape = ctx.meta
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the input image (multi-step rollout) is not implemented yet")
+        dx = dx.contiguous().view(B * H * W, E)
+        dpos = ops.pos_embed_grad(dx, B, H * W, E).view(1, E, H, W) if has_pos else None
+        dz0, dgamma, dbeta, dbias = ops.ln_residual_bwd(dx, z0, stats, norm_w.detach(), None, H * W, mode)
+        K = patches.shape[1]
+        dw = torch.zeros((E, K), dtype=torch.float32, device=dx.device)
+        ops.gemm(mode, dz0, 1, patches, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(E, K, dz0.shape[0]))
+        return None, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None
+
+
+# ---- one SwinV2 block ------------------------------------------------------------------------------------
+class SwinBlockFn(torch.autograd.Function):
+    """reference: SwinTransformerV2CrBlock.forward (swinv2_global.py:480-497) with the attention module
+    (:170-201 / :289-321), shift/partition/reverse (:446-478) and timm Mlp folded in.
+
+    Inputs: x fp32 (B,H,W,C) residual stream, xb its activation-type shadow, `scale` =
+    exp(min(logit_scale, ln 100)) (heads,), `bias` = CPB table (heads, L, L) or None, and
+    `dp1`/`dp2` = per-sample DropPath multipliers (B,) or None."""
+
+    @staticmethod
+    def forward(ctx, x, xb, scale, bias, qkv_w, qkv_b, proj_w, proj_b, n1_w, n1_b, fc1_w, fc1_b, fc2_w, fc2_b, n2_w, n2_b,
+                dp1, dp2, geom, mode: ComputeMode):
+        B, H, W, C = x.shape
+        heads, Wh, Ww, s0, s1 = geom
+        T = B * H * W
+        x2 = x.contiguous().view(T, C)
+        if mode.act_dtype == torch.float32:
+            xb = x2
+        wq, wp = SHADOWS.get(qkv_w, mode), SHADOWS.get(proj_w, mode)
+        w1, w2 = SHADOWS.get(fc1_w, mode), SHADOWS.get(fc2_w, mode)
+        scale_c = scale.detach().contiguous()
+        bias_c = None if bias is None else bias.detach().contiguous()
+        # attention branch
+        qkv = ops.gemm(mode, xb, 0, wq, 0, EPI_BIAS, bias=qkv_b.detach())                       # (T, 3C)
+        inv_norm = ops.qk_normalize_(qkv, C, heads)
+        o, lse = ops.window_attn_fwd(qkv, scale_c, bias_c, B, H, W, C, heads, Wh, Ww, s0, s1, mode)
+        z1 = ops.gemm(mode, o, 0, wp, 0, EPI_BIAS, bias=proj_b.detach())                         # (T, C)
+        x_mid, xb_mid, st1 = ops.ln_residual_fwd(z1, x2, n1_w.detach(), n1_b.detach(), dp1, None, H * W, mode)
+        # MLP branch
+        g, h = ops.gemm(mode, xb_mid, 0, w1, 0, EPI_BIAS_GELU, bias=fc1_b.detach())             # (T, hidden) x2
+        z2 = ops.gemm(mode, g, 0, w2, 0, EPI_BIAS, bias=fc2_b.detach())
+        x_out, xb_out, st2 = ops.ln_residual_fwd(z2, x_mid, n2_w.detach(), n2_b.detach(), dp2, None, H * W, mode)
+        ctx.save_for_backward(xb, qkv, inv_norm, lse, o, z1, st1, xb_mid, h, g, z2, st2, scale_c, bias_c, qkv_w, proj_w,
+                              fc1_w, fc2_w, n1_w, n2_w, dp1, dp2)
+        ctx.meta = (B, H, W, C, geom, mode)
+        shadow = xb_out if mode.act_dtype != torch.float32 else x_out.new_empty(0)
+        ctx.mark_non_differentiable(shadow)
+        return x_out.view(B, H, W, C), shadow
+
+    @staticmethod
+    def backward(ctx, dx_out, _dxb):
+        (xb, qkv, inv_norm, lse, o, z1, st1, xb_mid, h, g, z2, st2, scale_c, bias_c, qkv_w, proj_w, fc1_w, fc2_w, n1_w, n2_w,
+         dp1, dp2) = ctx.saved_tensors
+        B, H, W, C, geom, mode = ctx.meta
+        heads, Wh, Ww, s0, s1 = geom
+        T = B * H * W
+        hid = h.shape[1]
+        dev = dx_out.device
+        wq, wp = SHADOWS.get(qkv_w, mode), SHADOWS.get(proj_w, mode)
+        w1, w2 = SHADOWS.get(fc1_w, mode), SHADOWS.get(fc2_w, mode)
+        dx_out = dx_out.contiguous().view(T, C)
+
+        def wgrad(dy, act_in, n_out, n_in):
+            dw = torch.zeros((n_out, n_in), dtype=torch.float32, device=dev)
+            ops.gemm(mode, dy, 1, act_in, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(n_out, n_in, T))
+            return dw
+
+        # ---- MLP branch: x_out = x_mid + dp2 * LN2(fc2(gelu(fc1(xb_mid))))
+        dz2, dg2, db2, dbias_fc2 = ops.ln_residual_bwd(dx_out, z2, st2, n2_w.detach(), dp2, H * W, mode)
+        dh = ops.gemm(mode, dz2, 0, w2, 1, EPI_DGELU, aux=h)                                     # (T, hidden)
+        dw_fc2 = wgrad(dz2, g, C, hid)
+        dbias_fc1 = ops.colsum(dh)
+        dx_mid = ops.gemm(mode, dh, 0, w1, 1, EPI_ADD_F32, aux=dx_out)                           # fp32 (T, C)
+        dw_fc1 = wgrad(dh, xb_mid, hid, C)
+        del dh
+        # ---- attention branch: x_mid = x + dp1 * LN1(proj(attn(qkv(xb))))
+        dz1, dg1, db1, dbias_proj = ops.ln_residual_bwd(dx_mid, z1, st1, n1_w.detach(), dp1, H * W, mode)
+        d_o = ops.gemm(mode, dz1, 0, wp, 1, EPI_BIAS)                                            # (T, C)
+        dw_proj = wgrad(dz1, o, C, C)
+        dqkv, dscale, dbias_tab = ops.window_attn_bwd(qkv, inv_norm, scale_c, bias_c, o, d_o, lse, B, H, W, C, heads, Wh, Ww,
+                                                       s0, s1, mode)
+        dbias_qkv = ops.colsum(dqkv)
+        dx_in = ops.gemm(mode, dqkv, 0, wq, 1, EPI_ADD_F32, aux=dx_mid)                          # fp32 (T, C)
+        dw_qkv = wgrad(dqkv, xb, 3 * C, C)
+        return (dx_in.view(B, H, W, C), None, dscale, dbias_tab, dw_qkv, dbias_qkv, dw_proj, dbias_proj, dg1, db1, dw_fc1,
+                dbias_fc1, dw_fc2, dbias_fc2, dg2, db2, None, None, None, None)
+
+
+# ---- head + unpatchify (+ skip) ------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """reference: forward_head + `x + skip[:, :out_chans]` (swinv2_global.py:784-803)."""
+
+    @staticmethod
+    def forward(ctx, x, xb, head_w, skip, out_chans: int, patch: int, mode: ComputeMode):
+        B, H, W, C = x.shape
+        if mode.act_dtype == torch.float32:
+            xb = x.contiguous().view(B * H * W, C)
+        wh = SHADOWS.get(head_w, mode)
+        y = ops.gemm(mode, xb, 0, wh, 0, EPI_BIAS)                                               # (T, P*P*Co), cols (p,q,c)
+        out = ops.unpatchify(y, None if skip is None else skip.contiguous(), B, out_chans, H * patch, W * patch, patch)
+        ctx.save_for_backward(xb, head_w)
+        ctx.meta = (B, H, W, C, out_chans, patch, mode, skip is not None, None if skip is None else skip.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, head_w = ctx.saved_tensors
+        B, H, W, C, Co, patch, mode, has_skip, skip_ch = ctx.meta
+        wh = SHADOWS.get(head_w, mode)
+        dout = dout.contiguous()
+        dy = ops.patchify(dout, patch, 1, mode)                                                  # (T, P*P*Co)
+        dx = ops.gemm(mode, dy, 0, wh, 1, EPI_F32)                                               # fp32 (T, C)
+        N = head_w.shape[0]
+        dw = torch.zeros((N, C), dtype=torch.float32, device=dout.device)
+        ops.gemm(mode, dy, 1, xb, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(N, C, dy.shape[0]))
+        dskip = None
+        if has_skip and ctx.needs_input_grad[3]:
+            dskip = torch.zeros((B, skip_ch, H * patch, W * patch), dtype=torch.float32, device=dout.device)
+            dskip[:, :Co] = dout
+        return dx.view(B, H, W, C), None, dw, dskip, None, None, None
+
+
+# ---- loss ---------------------------------------------------------------------------------------------------------
+class LatWeightedL2Fn(torch.autograd.Function):
+    """reference: GeometricLpLoss.rel / .abs with p=2, squared (utils/losses.py:188-232) over
+    GridQuadrature 'naive' weights (utils/grids.py:68-117).  Returns a 0-d loss (sum over batch and channel)."""
+
+    @staticmethod
+    def forward(ctx, prd, tar, qw, chw, relative: bool, squared: bool):
+        prd, tar = prd.contiguous(), tar.contiguous()
+        loss, num, den = ops.latw_l2_fwd(prd, tar, qw, chw, relative, squared)
+        ctx.save_for_backward(prd, tar, qw, chw, num, den)
+        ctx.flags = (relative, squared)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        prd, tar, qw, chw, num, den = ctx.saved_tensors
+        g = gloss.detach().to(torch.float32).reshape(1).contiguous()
+        dprd = ops.latw_l2_bwd(prd, tar, qw, chw, num, den, g, *ctx.flags)
+        return dprd, None, None, None, None, None

@@ -1,0 +1,242 @@
+"""Tensor-level wrappers over the C ABI (include/swinb200.h).
+
+PyTorch is used here for device memory, streams and shape bookkeeping only: every arithmetic
+operation below is one of our CUDA kernels, launched on torch's current stream.  Arguments are
+validated (device, dtype, contiguity) before their raw pointers cross the ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (BACKEND_SIMT, BACKEND_TCGEN05, BF16, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_F32, F32,
+                   SwinB200Error)
+
+LN_EPS = 1e-5
+
+
+@dataclass(frozen=True)
+class ComputeMode:
+    """How the hot path computes.
+
+    bf16 : activations stored in bf16, fp32 residual stream / statistics / accumulators, tcgen05 GEMMs.
+    fp32 : fp32 storage and CUDA-core fp32 arithmetic everywhere (validation mode, parity <= 1e-5).
+    `gemm_backend` / `attn_backend` select CUDA-core or tcgen05 kernels (tcgen05 needs bf16).
+    """
+    name: str
+    act_dtype: torch.dtype
+    gemm_backend: int
+    attn_backend: int
+
+    @property
+    def act_code(self) -> int:
+        return BF16 if self.act_dtype == torch.bfloat16 else F32
+
+
+MODE_BF16 = ComputeMode("bf16", torch.bfloat16, BACKEND_TCGEN05, BACKEND_SIMT)
+MODE_BF16_SIMT = ComputeMode("bf16_simt", torch.bfloat16, BACKEND_SIMT, BACKEND_SIMT)
+MODE_FP32 = ComputeMode("fp32", torch.float32, BACKEND_SIMT, BACKEND_SIMT)
+MODES = {m.name: m for m in (MODE_BF16, MODE_BF16_SIMT, MODE_FP32)}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], name: str, dtype=None, allow_none=False) -> int:
+    if t is None:
+        if allow_none:
+            return 0
+        raise SwinB200Error(f"{name}: tensor is required")
+    if not t.is_cuda:
+        raise SwinB200Error(f"{name}: expected a CUDA tensor, got {t.device}")
+    if not t.is_contiguous():
+        raise SwinB200Error(f"{name}: tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise SwinB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return BF16
+    if dtype == torch.float32:
+        return F32
+    raise SwinB200Error(f"unsupported storage dtype {dtype}")
+
+
+# ---- parameter staging -------------------------------------------------------------------------------
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _lib.call("swinb200_cast_f32_to_bf16", _chk(src, "src", torch.float32), _chk(out, "out", torch.bfloat16), src.numel(), _stream())
+    return out
+
+
+def to_act(x: torch.Tensor, mode: ComputeMode) -> torch.Tensor:
+    """fp32 tensor -> activation storage type (alias in fp32 mode)."""
+    return x if mode.act_dtype == torch.float32 else cast_bf16(x)
+
+
+# ---- patchify / unpatchify ---------------------------------------------------------------------------
+def patchify(img: torch.Tensor, patch: int, order: int, mode: ComputeMode) -> torch.Tensor:
+    B, C, Hi, Wi = img.shape
+    T = B * (Hi // patch) * (Wi // patch)
+    out = torch.empty((T, C * patch * patch), dtype=mode.act_dtype, device=img.device)
+    _lib.call("swinb200_patchify", _chk(img, "img", torch.float32), out.data_ptr(), mode.act_code, B, C, Hi, Wi, patch, order, _stream())
+    return out
+
+
+def unpatchify(y: torch.Tensor, skip: Optional[torch.Tensor], B: int, Co: int, Hi: int, Wi: int, patch: int) -> torch.Tensor:
+    out = torch.empty((B, Co, Hi, Wi), dtype=torch.float32, device=y.device)
+    skip_ch = 0 if skip is None else skip.shape[1]
+    _lib.call("swinb200_unpatchify", _chk(y, "y"), _code(y.dtype), _chk(skip, "skip", torch.float32, True), skip_ch, out.data_ptr(),
+              B, Co, Hi, Wi, patch, _stream())
+    return out
+
+
+# ---- GEMM ------------------------------------------------------------------------------------------
+def gemm(mode: ComputeMode, A: torch.Tensor, a_major: int, B: torch.Tensor, b_major: int, epilogue: int, *,
+         bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out2: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1, backend: Optional[int] = None):
+    """D[M,N] = epi(sum_k A(m,k) B(n,k)); see swinb200_gemm.  A/B are 2-D contiguous tensors."""
+    if a_major == 0:
+        M, K = A.shape
+    else:
+        K, M = A.shape
+    if b_major == 0:
+        N, Kb = B.shape
+    else:
+        Kb, N = B.shape
+    if K != Kb:
+        raise SwinB200Error(f"gemm: reduction sizes differ ({K} vs {Kb})")
+    if A.dtype != B.dtype:
+        raise SwinB200Error("gemm: A and B must share a storage dtype")
+    f32_out = epilogue in (EPI_ADD_F32, EPI_F32)
+    out_dtype = torch.float32 if f32_out else A.dtype
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    if epilogue == EPI_BIAS_GELU and out2 is None:
+        out2 = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    be = mode.gemm_backend if backend is None else backend
+    _lib.call("swinb200_gemm", be, M, N, K, _chk(A, "A"), a_major, A.shape[1], _chk(B, "B"), b_major, B.shape[1], _code(A.dtype),
+              epilogue, _chk(bias, "bias", torch.float32, True), _chk(out, "out", out_dtype), out.shape[1],
+              _chk(out2, "out2", out_dtype, True), _chk(aux, "aux", None, True), 0 if aux is None else aux.shape[1],
+              _code(out_dtype), int(accumulate), int(split_k), _stream())
+    return (out, out2) if epilogue == EPI_BIAS_GELU else out
+
+
+def wgrad_split_k(M: int, N: int, K: int) -> int:
+    """Split-K factor so a weight-gradient GEMM (few output tiles, K = tokens) fills the 148 SMs."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    kb = (K + 63) // 64
+    best = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
+    return best
+
+
+# ---- LayerNorm + residual ------------------------------------------------------------------------------
+def ln_residual_fwd(z, x_in, gamma, beta, sample_scale, pos, rows_per_sample: int, mode: ComputeMode):
+    rows, C = z.shape
+    x_out = torch.empty((rows, C), dtype=torch.float32, device=z.device)
+    xb = x_out if mode.act_dtype == torch.float32 else torch.empty((rows, C), dtype=mode.act_dtype, device=z.device)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=z.device)
+    _lib.call("swinb200_ln_residual_fwd", _chk(z, "z", mode.act_dtype), mode.act_code, _chk(x_in, "x_in", torch.float32, True),
+              _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32),
+              _chk(sample_scale, "sample_scale", torch.float32, True), _chk(pos, "pos", torch.float32, True),
+              x_out.data_ptr(), xb.data_ptr(), stats.data_ptr(), rows, C, rows_per_sample, LN_EPS, _stream())
+    return x_out, xb, stats
+
+
+def ln_residual_bwd(dx, z, stats, gamma, sample_scale, rows_per_sample: int, mode: ComputeMode, want_dbias_prev=True):
+    rows, C = z.shape
+    dz = torch.empty((rows, C), dtype=mode.act_dtype, device=z.device)
+    acc = torch.zeros((3, C), dtype=torch.float32, device=z.device)
+    _lib.call("swinb200_ln_residual_bwd", _chk(dx, "dx", torch.float32), _chk(z, "z", mode.act_dtype), mode.act_code,
+              _chk(stats, "stats", torch.float32), _chk(gamma, "gamma", torch.float32),
+              _chk(sample_scale, "sample_scale", torch.float32, True), dz.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(),
+              acc[2].data_ptr() if want_dbias_prev else 0, rows, C, rows_per_sample, _stream())
+    return dz, acc[0], acc[1], acc[2]
+
+
+def transpose_f32(src: torch.Tensor) -> torch.Tensor:
+    R, Cc = src.shape
+    dst = torch.empty((Cc, R), dtype=torch.float32, device=src.device)
+    _lib.call("swinb200_transpose_f32", _chk(src, "src", torch.float32), dst.data_ptr(), R, Cc, _stream())
+    return dst
+
+
+def pos_embed_grad(dx: torch.Tensor, B: int, rows_per_sample: int, C: int) -> torch.Tensor:
+    dpos = torch.empty((C, rows_per_sample), dtype=torch.float32, device=dx.device)
+    _lib.call("swinb200_pos_embed_grad", _chk(dx, "dx", torch.float32), dpos.data_ptr(), B, rows_per_sample, C, _stream())
+    return dpos
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    out = torch.zeros((cols,), dtype=torch.float32, device=x.device)
+    _lib.call("swinb200_colsum", _chk(x, "x"), _code(x.dtype), out.data_ptr(), rows, cols, cols, _stream())
+    return out
+
+
+# ---- attention --------------------------------------------------------------------------------------------
+def qk_normalize_(qkv: torch.Tensor, C: int, heads: int) -> torch.Tensor:
+    T = qkv.shape[0]
+    inv_norm = torch.empty((T, 2, heads), dtype=torch.float32, device=qkv.device)
+    _lib.call("swinb200_qk_normalize", _chk(qkv, "qkv"), _code(qkv.dtype), inv_norm.data_ptr(), T, C, heads, _stream())
+    return inv_norm
+
+
+def shift_mask(H, W, Wh, Ww, s0, s1, device) -> torch.Tensor:
+    nW, L = (H // Wh) * (W // Ww), Wh * Ww
+    mask = torch.empty((nW, L, L), dtype=torch.float32, device=device)
+    _lib.call("swinb200_shift_mask", mask.data_ptr(), H, W, Wh, Ww, s0, s1, _stream())
+    return mask
+
+
+def window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, Wh, Ww, s0, s1, mode: ComputeMode, backend=None):
+    T = B * H * W
+    nW, L = (H // Wh) * (W // Ww), Wh * Ww
+    o = torch.empty((T, C), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((B, nW, heads, L), dtype=torch.float32, device=qkv.device)
+    _lib.call("swinb200_window_attn_fwd", mode.attn_backend if backend is None else backend, _chk(qkv, "qkv"), _code(qkv.dtype),
+              _chk(scale, "scale", torch.float32), _chk(bias, "bias", torch.float32, True), o.data_ptr(), lse.data_ptr(),
+              B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
+    return o, lse
+
+
+def window_attn_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, B, H, W, C, heads, Wh, Ww, s0, s1, mode: ComputeMode,
+                    backend=None):
+    L = Wh * Ww
+    dqkv = torch.empty_like(qkv)
+    dscale = torch.zeros((heads,), dtype=torch.float32, device=qkv.device)
+    dbias = torch.zeros((heads, L, L), dtype=torch.float32, device=qkv.device) if bias is not None else None
+    _lib.call("swinb200_window_attn_bwd", mode.attn_backend if backend is None else backend, _chk(qkv, "qkv"), _code(qkv.dtype),
+              _chk(inv_norm, "inv_norm", torch.float32), _chk(scale, "scale", torch.float32),
+              _chk(bias, "bias", torch.float32, True), _chk(o, "o", qkv.dtype), _chk(d_o, "d_o", qkv.dtype),
+              _chk(lse, "lse", torch.float32), dqkv.data_ptr(), dscale.data_ptr(), 0 if dbias is None else dbias.data_ptr(),
+              B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
+    return dqkv, dscale, dbias
+
+
+# ---- loss ---------------------------------------------------------------------------------------------------
+def latw_l2_fwd(prd, tar, qw, chw, relative: bool, squared: bool = True):
+    B, C, H, W = prd.shape
+    num = torch.empty((B * C,), dtype=torch.float32, device=prd.device)
+    den = torch.empty((B * C,), dtype=torch.float32, device=prd.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=prd.device)
+    _lib.call("swinb200_latw_l2_fwd", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
+              _chk(chw, "chw", torch.float32), int(relative), int(squared), num.data_ptr(), den.data_ptr(), loss.data_ptr(), B, C, H, W, _stream())
+    return loss, num, den
+
+
+def latw_l2_bwd(prd, tar, qw, chw, num, den, gloss, relative: bool, squared: bool = True):
+    B, C, H, W = prd.shape
+    dprd = torch.empty_like(prd)
+    _lib.call("swinb200_latw_l2_bwd", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
+              _chk(chw, "chw", torch.float32), _chk(num, "num", torch.float32), _chk(den, "den", torch.float32),
+              _chk(gloss, "gloss", torch.float32), int(relative), int(squared), dprd.data_ptr(), B, C, H, W, _stream())
+    return dprd

@@ -1,0 +1,304 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes), against the CPU oracle
+(`oracle/swinv2_oracle.py`) or an fp32 torch restatement of the same op on the same seeded inputs.
+
+Tolerances: fp32 storage -> 1e-5 relative L2 (the north-star fp32 validation bound); bf16 storage ->
+1e-2 relative L2 (the bf16 bound); integer / mask work -> bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import swinv2_oracle as O
+from swin_v2_weather_b200 import ops
+from swin_v2_weather_b200._lib import (BACKEND_SIMT, BACKEND_TCGEN05, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU,
+                                        EPI_F32)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2}
+
+
+def rel(a, b):
+    return O.rel_l2(a.float(), b.float())
+
+
+def mode_for(dtype, tc=False):
+    if dtype == torch.float32:
+        return ops.MODE_FP32
+    return ops.MODE_BF16 if tc else ops.MODE_BF16_SIMT
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_cast_bf16():
+    for n in (8, 1000, 12345, 1 << 20):
+        x = gen(n, seed=n)
+        assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("order", [0, 1])
+def test_patchify(dtype, order):
+    B, C, Hi, Wi, P = 2, 7, 72, 144, 4
+    x = gen(B, C, Hi, Wi, seed=1)
+    got = ops.patchify(x, P, order, mode_for(dtype))
+    H, W = Hi // P, Wi // P
+    v = x.view(B, C, H, P, W, P)
+    if order == 0:   # columns (c, p, q): Conv2d im2col
+        want = v.permute(0, 2, 4, 1, 3, 5).reshape(B * H * W, C * P * P)
+    else:            # columns (p, q, c): inverse of the head's unpatchify
+        want = v.permute(0, 2, 4, 3, 5, 1).reshape(B * H * W, C * P * P)
+    assert torch.equal(got, want.to(dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_skip", [False, True])
+def test_unpatchify(dtype, with_skip):
+    B, Co, Hi, Wi, P = 2, 5, 72, 144, 4
+    H, W = Hi // P, Wi // P
+    y = gen(B * H * W, P * P * Co, seed=2).to(dtype)
+    skip = gen(B, 7, Hi, Wi, seed=3) if with_skip else None
+    got = ops.unpatchify(y, skip, B, Co, Hi, Wi, P)
+    want = y.float().view(B, H, W, P, P, Co).permute(0, 5, 1, 3, 2, 4).reshape(B, Co, Hi, Wi)
+    if with_skip:
+        want = want + skip[:, :Co]
+    assert torch.equal(got, want)
+
+
+def test_transpose_and_pos_grad():
+    src = gen(650, 200, seed=4)
+    assert torch.equal(ops.transpose_f32(src), src.t().contiguous())
+    dx = gen(3, 648, 96, seed=5)
+    got = ops.pos_embed_grad(dx.view(3 * 648, 96), 3, 648, 96)
+    assert rel(got, dx.sum(0).t()) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [96, 192, 768])
+def test_ln_residual_fwd_bwd(dtype, C):
+    mode = mode_for(dtype)
+    B, rps = 2, 300
+    rows = B * rps
+    z = gen(rows, C, seed=6).to(dtype)
+    x_in = gen(rows, C, seed=7)
+    gamma, beta = 1 + 0.1 * gen(C, seed=8), 0.1 * gen(C, seed=9)
+    ss = torch.tensor([0.0, 1.0 / 0.9], device=DEV)
+    pos = gen(rps, C, seed=10)
+    for use_x, use_ss, use_pos in ((True, True, False), (False, False, True), (True, False, False)):
+        x_out, xb, stats = ops.ln_residual_fwd(z, x_in if use_x else None, gamma, beta, ss if use_ss else None,
+                                               pos if use_pos else None, rps, mode)
+        zf = z.float().requires_grad_(True)
+        gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        u = torch.nn.functional.layer_norm(zf, (C,), gf, bf, 1e-5)
+        if use_pos:
+            u = u + pos.repeat(B, 1)
+        if use_ss:
+            u = u * ss.repeat_interleave(rps).view(-1, 1)
+        want = (x_in if use_x else 0) + u
+        assert rel(x_out, want) < 1e-6
+        assert torch.equal(xb.float(), x_out.to(dtype).float())
+        dx = gen(rows, C, seed=11)
+        dz, dg, db, dbp = ops.ln_residual_bwd(dx, z, stats, gamma, ss if use_ss else None, rps, mode)
+        want.backward(dx)
+        assert rel(dz, zf.grad) < TOL[dtype]
+        assert rel(dg, gf.grad) < 1e-5 and rel(db, bf.grad) < 1e-5
+        assert rel(dbp, dz.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum(dtype):
+    for rows, cols in ((1000, 768), (333, 3072), (64, 8)):
+        x = gen(rows, cols, seed=12).to(dtype)
+        assert rel(ops.colsum(x), x.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("heads,C", [(8, 768), (2, 192), (4, 768), (12, 768), (16, 768)])
+def test_qk_normalize(dtype, heads, C):
+    T = 500
+    qkv0 = gen(T, 3 * C, seed=13).to(dtype)
+    qkv = qkv0.clone()
+    inv = ops.qk_normalize_(qkv, C, heads)
+    d = C // heads
+    ref = qkv0.float().view(T, 3, heads, d)
+    nrm = ref[:, :2].norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    want = ref.clone()
+    want[:, :2] = ref[:, :2] / nrm
+    assert rel(qkv.view(T, 3, heads, d)[:, :2], want[:, :2]) < (1e-6 if dtype == torch.float32 else 4e-3)
+    assert torch.equal(qkv.view(T, 3, heads, d)[:, 2], qkv0.view(T, 3, heads, d)[:, 2])   # v untouched
+    assert rel(inv, 1.0 / nrm.squeeze(-1)) < 1e-6
+
+
+def test_shift_mask_bit_exact():
+    for (H, W, Wh, Ww, s0, s1) in ((18, 36, 9, 18, 4, 9), (180, 360, 9, 18, 4, 9), (12, 24, 6, 12, 3, 6), (18, 36, 18, 18, 0, 9)):
+        got = ops.shift_mask(H, W, Wh, Ww, s0, s1, DEV).cpu()
+        want = O.shift_attention_mask((H, W), (Wh, Ww), (s0, s1))
+        assert torch.equal(got, want), (H, W, Wh, Ww, s0, s1)
+
+
+# ---- attention ----------------------------------------------------------------------------------------------
+def oracle_attention(qkv_raw, scale, bias, B, H, W, C, heads, window, shift):
+    """q/k/v (T, 3C) fp32 raw -> (o (T, C), grads fn) with the oracle's index arithmetic."""
+    idx = O.window_token_index((H, W), window, shift).to(qkv_raw.device)
+    nW, L = idx.shape
+    d = C // heads
+    tok = qkv_raw.view(B, H * W, 3, heads, d)
+    w = tok[:, idx.reshape(-1)].view(B, nW, L, 3, heads, d).permute(3, 0, 1, 4, 2, 5)   # 3,B,nW,h,L,d
+    q, k, v = w[0], w[1], w[2]
+    qn = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    kn = k / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    s = (qn @ kn.transpose(-1, -2)) * scale.view(1, 1, heads, 1, 1)
+    if bias is not None:
+        s = s + bias.view(1, 1, heads, L, L)
+    mask = O.shift_attention_mask((H, W), window, shift)
+    if mask is not None:
+        s = s + mask.to(s).view(1, nW, 1, L, L)
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).permute(0, 1, 3, 2, 4).reshape(B, nW * L, C)
+    out = torch.empty(B, H * W, C, device=o.device, dtype=o.dtype)
+    out[:, idx.reshape(-1)] = o
+    lse = torch.logsumexp(s, dim=-1)
+    return out.reshape(B * H * W, C), lse
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, H=18, W=36, C=192, heads=2, window=(9, 18), shift=(0, 0), bias=False),
+    dict(B=2, H=18, W=36, C=192, heads=2, window=(9, 18), shift=(4, 9), bias=False),
+    dict(B=1, H=18, W=36, C=192, heads=2, window=(9, 18), shift=(4, 9), bias=True),
+    dict(B=1, H=12, W=24, C=128, heads=2, window=(6, 12), shift=(3, 6), bias=True),
+])
+def test_window_attention_simt(dtype, cfg):
+    B, H, W, C, heads = cfg["B"], cfg["H"], cfg["W"], cfg["C"], cfg["heads"]
+    window, shift = cfg["window"], cfg["shift"]
+    L = window[0] * window[1]
+    mode = mode_for(dtype)
+    T = B * H * W
+    raw = gen(T, 3 * C, seed=20).to(dtype)
+    scale = torch.tensor([10.0, 37.0][:heads], device=DEV)
+    bias = (0.5 * gen(heads, L, L, seed=21)) if cfg["bias"] else None
+    # oracle (fp32, autograd) on the same stored values
+    raw_f = raw.float().requires_grad_(True)
+    sc_f = scale.clone().requires_grad_(True)
+    b_f = bias.clone().requires_grad_(True) if bias is not None else None
+    o_ref, lse_ref = oracle_attention(raw_f, sc_f, b_f, B, H, W, C, heads, window, shift)
+    # ours
+    qkv = raw.clone()
+    inv = ops.qk_normalize_(qkv, C, heads)
+    o, lse = ops.window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, window[0], window[1], shift[0], shift[1], mode)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert rel(o, o_ref) < tol
+    assert rel(lse.view(-1), lse_ref.reshape(-1)) < tol
+    d_o = gen(T, C, seed=22).to(dtype)
+    dqkv, dscale, dbias = ops.window_attn_bwd(qkv, inv, scale, bias, o, d_o, lse, B, H, W, C, heads, window[0], window[1],
+                                              shift[0], shift[1], mode)
+    o_ref.backward(d_o.float())
+    assert rel(dqkv, raw_f.grad) < (5e-5 if dtype == torch.float32 else 2e-2)
+    assert rel(dscale, sc_f.grad) < (5e-5 if dtype == torch.float32 else 2e-2)
+    if bias is not None:
+        assert rel(dbias, b_f.grad) < (5e-5 if dtype == torch.float32 else 2e-2)
+
+
+# ---- loss ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("relative", [True, False])
+@pytest.mark.parametrize("squared", [True, False])
+def test_latw_l2(relative, squared):
+    B, C, H, W = 2, 5, 72, 144
+    prd = gen(B, C, H, W, seed=30).requires_grad_(True)
+    tar = gen(B, C, H, W, seed=31)
+    chw = torch.rand(C, generator=torch.Generator().manual_seed(32)).to(DEV)
+    qw = O.quadrature_row_weights(H, W).to(DEV)
+    loss, num, den = ops.latw_l2_fwd(prd.detach(), tar, qw, chw, relative, squared)
+    want = O.geometric_l2(prd, tar, chw, relative, squared)
+    assert abs(float(loss) - float(want)) / abs(float(want)) < 1e-5
+    g = torch.tensor([0.7], device=DEV)
+    dprd = ops.latw_l2_bwd(prd.detach(), tar, qw, chw, num, den, g, relative, squared)
+    (want * 0.7).backward()
+    assert rel(dprd, prd.grad) < 1e-5
+
+
+# ---- GEMM ------------------------------------------------------------------------------------------------------
+def gemm_reference(A, a_major, Bm, b_major, epi, bias, aux, dtype):
+    Af = A.float() if a_major == 0 else A.float().t()
+    Bf = Bm.float() if b_major == 0 else Bm.float().t()
+    acc = (Af.double() @ Bf.double().t()).float()
+    rnd = (lambda t: t.to(dtype).float())
+    if epi == EPI_BIAS:
+        return acc + (bias if bias is not None else 0)
+    if epi == EPI_BIAS_GELU:
+        h = acc + bias
+        return torch.nn.functional.gelu(rnd(h)), h
+    if epi == EPI_DGELU:
+        h = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(h).sum().backward()
+        return acc * h.grad
+    if epi == EPI_ADD_F32:
+        return acc + aux
+    return acc
+
+
+GEMM_CASES = [
+    # (M, N, K, a_major, b_major, epilogue)
+    (300, 192, 96, 0, 0, EPI_BIAS),
+    (1000, 2304, 768, 0, 0, EPI_BIAS),
+    (777, 3072, 768, 0, 0, EPI_BIAS_GELU),
+    (640, 768, 1168, 0, 0, EPI_BIAS),       # patch-embed shape: K tail
+    (650, 1168, 768, 0, 0, EPI_BIAS),       # head shape: N tail
+    (515, 768, 3072, 0, 1, EPI_DGELU),
+    (515, 768, 2304, 0, 1, EPI_ADD_F32),
+    (515, 768, 768, 0, 1, EPI_BIAS),
+    (515, 768, 1168, 0, 1, EPI_F32),
+    (768, 3072, 1000, 1, 1, EPI_F32),       # wgrad, K tail
+    (2304, 768, 1300, 1, 1, EPI_F32),
+    (1168, 768, 648, 1, 1, EPI_F32),        # head wgrad: M tail
+]
+
+
+def run_gemm_case(case, dtype, backend, split_k=1):
+    M, N, K, a_major, b_major, epi = case
+    mode = mode_for(dtype)
+    A = gen(*((M, K) if a_major == 0 else (K, M)), seed=40, scale=0.5).to(dtype)
+    Bm = gen(*((N, K) if b_major == 0 else (K, N)), seed=41, scale=0.5).to(dtype)
+    bias = gen(N, seed=42) if epi in (EPI_BIAS, EPI_BIAS_GELU) else None
+    aux = None
+    if epi == EPI_DGELU:
+        aux = gen(M, N, seed=43).to(dtype)
+    elif epi == EPI_ADD_F32:
+        aux = gen(M, N, seed=43)
+    kw = {}
+    if epi == EPI_F32 and split_k > 1:
+        kw = dict(out=torch.zeros(M, N, device=DEV), accumulate=True, split_k=split_k)
+    got = ops.gemm(mode, A, a_major, Bm, b_major, epi, bias=bias, aux=aux, backend=backend, **kw)
+    want = gemm_reference(A, a_major, Bm, b_major, epi, bias, aux, dtype)
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    if epi == EPI_BIAS_GELU:
+        assert rel(got[0], want[0]) < tol and rel(got[1], want[1]) < tol
+    else:
+        assert rel(got, want) < (1e-5 if epi in (EPI_ADD_F32, EPI_F32) else tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_simt(case, dtype):
+    run_gemm_case(case, dtype, BACKEND_SIMT)
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_tcgen05(case):
+    run_gemm_case(case, torch.bfloat16, BACKEND_TCGEN05)
+
+
+@pytest.mark.parametrize("split_k", [2, 5, 16])
+def test_gemm_tcgen05_split_k(split_k):
+    run_gemm_case((768, 3072, 4000, 1, 1, EPI_F32), torch.bfloat16, BACKEND_TCGEN05, split_k)
+
+
+def test_gemm_tcgen05_persistent_many_tiles():
+    # more tiles than SMs: exercises the TMEM double buffering and the smem ring wrap-around
+    run_gemm_case((128 * 40, 2304, 768, 0, 0, EPI_BIAS), torch.bfloat16, BACKEND_TCGEN05)
+    run_gemm_case((128 * 40 + 17, 3072, 768, 0, 0, EPI_BIAS_GELU), torch.bfloat16, BACKEND_TCGEN05)
