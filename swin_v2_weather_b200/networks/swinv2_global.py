@@ -403,7 +403,7 @@ class SwinTransformerV2Cr(nn.Module):
         self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
                                       norm_layer=norm_layer)
         patch_grid_size = self.patch_embed.grid_size
-        dpr = [x.tolist() for x in torch.linspace(0, drop_path_rate, sum(depths)).split(depths)]
+        dpr = [x.tolist() for x in torch.linspace(0, drop_path_rate, sum(depths), device="cpu").split(depths)]
         stages = []
         for stage_idx, (depth, heads) in enumerate(zip(depths, num_heads)):
             stages += [SwinTransformerV2CrStage(

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/swinb200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from swin_v2_weather_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "swinb200.h")).read()
+    return sorted(set(re.findall(r"\b(swinb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    if not os.path.exists(_lib.LIB_PATH):
+        from swin_v2_weather_b200.build import build
+        build()
+    lib = _lib.load()
+    assert lib.swinb200_version() == 100
+    syms = declared_symbols()
+    assert len(syms) >= 17
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in swinb200.h but not exported"
+    # every prototype bound by the Python side is declared in the header, and vice versa
+    bound = set(_lib.PROTOTYPES) | {"swinb200_version", "swinb200_last_error"}
+    assert bound == set(syms), bound ^ set(syms)
+
+
+def test_argument_errors_come_back_as_codes_not_crashes():
+    lib = _lib.load()
+    # null pointers / bad shapes are rejected before any CUDA call
+    assert lib.swinb200_cast_f32_to_bf16(None, None, 16, None) == 1
+    assert b"null" in lib.swinb200_last_error()
+    rc = lib.swinb200_gemm(0, 0, 8, 8, None, 0, 8, None, 0, 8, 0, 0, None, None, 8, None, None, 0, 0, 0, 1, None)
+    assert rc == 1 and b"bad shape" in lib.swinb200_last_error()
+    rc = lib.swinb200_patchify(ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 1, 3, 72, 144, 8, 0, None)
+    assert rc == 1 and b"patch_size 4" in lib.swinb200_last_error()
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """`tcgen05.mma` -> UTC*MMA, `tcgen05.ld` -> LDTM, TMA -> UTMALDG in the shipped binary."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "LDTM" in sass and "UTMALDG" in sass
+    assert "sm_100a" in sass

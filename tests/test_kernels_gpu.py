@@ -92,7 +92,7 @@ def test_ln_residual_fwd_bwd(dtype, C):
     for use_x, use_ss, use_pos in ((True, True, False), (False, False, True), (True, False, False)):
         x_out, xb, stats = ops.ln_residual_fwd(z, x_in if use_x else None, gamma, beta, ss if use_ss else None,
                                                pos if use_pos else None, rps, mode)
-        zf = z.float().requires_grad_(True)
+        zf = z.float().clone().requires_grad_(True)
         gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
         u = torch.nn.functional.layer_norm(zf, (C,), gf, bf, 1e-5)
         if use_pos:
