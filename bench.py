@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: training samples/s (fwd + loss + bwd) of the 73-channel, depth-12 SwinV2
+weather model on synthetic 73x721x1440 fields (cropped to 720 rows exactly as the reference loaders do),
+batch 1 per GPU, data-parallel over N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                    # our CUDA path (one JSON line)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               # the reference algorithm on the host CPU cores
+
+`value`      : whole-job samples/s with inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`        : same metric through the public model API from pinned HOST buffers: per step the H2D copy of that
+               step's input + target and the D2H read of the loss are inside the timed region.
+`roofline`   : the dominant kernel family, timed live with CUDA events inside the timed region.
+`cpu_baseline`: the CPU oracle (a port of the reference algorithm) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- workload (BASELINE.json configs[1]: swin_73var_geo_depth12, config/swin.yaml:145-150 over :2-16) ----
+CFG = dict(img_size=(720, 1440), patch_size=4, depth=12, num_heads=8, in_chans=73, out_chans=73, embed_dim=768,
+           window_ratio=80, drop_path_rate=0.1, full_pos_embed=True, rel_pos=False, mlp_ratio=4.0, residual=False)
+FIELD_ROWS = 721          # ERA5 rows on disk; the loaders crop [:720] (data_loader_era5.py:163-165)
+T = 180 * 360             # tokens per sample
+FLOPS_FWD_BWD = 34.96e12  # per sample, SURVEY section 8(a)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ---- clocks sampler ----------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- kernel-family timer (CUDA events on the launching stream, no syncs inside the timed region) ------------------
+class KernelTimer:
+    FAMILY = {"swinb200_gemm": "gemm", "swinb200_window_attn_fwd": "attn_fwd", "swinb200_window_attn_bwd": "attn_bwd",
+              "swinb200_ln_residual_fwd": "ln_fwd", "swinb200_ln_residual_bwd": "ln_bwd"}
+
+    def __init__(self):
+        self.records = []   # (family, flops, bytes, start_event, end_event)
+        self.enabled = False
+
+    @contextlib.contextmanager
+    def hook(self, name, args):
+        fam = self.FAMILY.get(name)
+        if not self.enabled or fam is None:
+            yield
+            return
+        flops = bytes_ = 0.0
+        if fam == "gemm":
+            backend, M, N, K = args[0], args[1], args[2], args[3]
+            fam = "gemm_tcgen05" if backend == 1 else "gemm_simt"
+            flops = 2.0 * M * N * K
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.append((fam, flops, bytes_, s, e))
+
+    def summary(self):
+        fam = {}
+        for f, fl, by, s, e in self.records:
+            d = fam.setdefault(f, dict(ms=0.0, flops=0.0, launches=0))
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["launches"] += 1
+        return fam
+
+
+def make_model(device, compute_mode="bf16"):
+    from swin_v2_weather_b200.networks.swinv2_global import SwinTransformerV2Cr
+    torch.manual_seed(0)
+    m = SwinTransformerV2Cr(img_size=CFG["img_size"], patch_size=4, depths=(CFG["depth"],), num_heads=(CFG["num_heads"],),
+                            in_chans=CFG["in_chans"], out_chans=CFG["out_chans"], embed_dim=CFG["embed_dim"],
+                            img_window_ratio=CFG["window_ratio"], drop_path_rate=CFG["drop_path_rate"],
+                            full_pos_embed=True, rel_pos=False, mlp_ratio=CFG["mlp_ratio"], residual=False,
+                            compute_mode=compute_mode)
+    with torch.no_grad():   # the reference zero-inits norm1/2.weight, which makes every block the identity
+        g = torch.Generator().manual_seed(1)
+        for blk in m.stages[0].blocks:
+            blk.norm1.weight.copy_(1 + 0.1 * torch.randn(768, generator=g))
+            blk.norm2.weight.copy_(1 + 0.1 * torch.randn(768, generator=g))
+    return m.to(device).train()
+
+
+def make_loss(device):
+    from types import SimpleNamespace
+    from swin_v2_weather_b200.utils.losses import LossHandler
+    p = SimpleNamespace(n_future=0, img_shape_x=720, img_shape_y=1440, loss='squared geometric l2', channel_weights='none',
+                        n_out_channels=73, channel_names=[], out_channels=list(range(73)), dt=1, model_grid_type='equiangular')
+    return LossHandler(p).to(device).train()
+
+
+# ==============================================================================================================
+# our arm
+# ==============================================================================================================
+def run_ours(args):
+    from swin_v2_weather_b200 import _lib, distributed as D
+    rank, world, local = D.init_from_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    peaks = read_peaks()
+    B = args.batch_per_gpu
+
+    model = make_model(dev, args.mode)
+    lossf = make_loss(dev)
+    ddp = D.wrap_ddp(model, local)
+    params = [p for p in model.parameters()]
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_x = torch.randn(B, 73, FIELD_ROWS, 1440, generator=gen).pin_memory()
+    host_t = torch.randn(B, 73, FIELD_ROWS, 1440, generator=gen).pin_memory()
+    x_res = host_x[:, :, :720].contiguous().to(dev)     # resident copies for the `value` leg (crop as the loaders do)
+    t_res = host_t[:, :, :720].contiguous().to(dev)
+
+    def step(x, t):
+        for p in params:
+            p.grad = None
+        pred = ddp(x)
+        loss = lossf(pred, t, x)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    timer = KernelTimer()
+    _lib.PROFILE_HOOK = timer.hook
+
+    # ---- leg 1: inputs resident in HBM -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(x_res, t_res)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCH_COUNT
+    timer.enabled = True
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        step(x_res, t_res)
+    ev[1].record()
+    barrier()
+    timer.enabled = False
+    ms_total = D.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
+    launches = _lib.LAUNCH_COUNT - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    fam = timer.summary()
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+    # ---- leg 2: end to end from pinned host buffers (prefetch on a copy stream, double-buffered) ---------------
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [(torch.empty(B, 73, 720, 1440, device=dev), torch.empty(B, 73, 720, 1440, device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    h2d_bytes = 2 * B * 73 * 720 * 1440 * 4
+
+    def prefetch(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            dx, dt = bufs[slot]
+            for b in range(B):
+                for c in range(73):     # crop [:720]: each plane's first 720 rows are one contiguous 4.1 MB run
+                    dx[b, c].copy_(host_x[b, c, :720], non_blocking=True)
+                    dt[b, c].copy_(host_t[b, c, :720], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            consumed[s].record()
+        prefetch(0)
+        last = None
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)
+            slot = i % 2
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss = step(*bufs[slot])
+            consumed[slot].record()
+            last = float(loss.item())          # D2H read of the step's result (the reference logs loss.item() per step)
+        return last
+
+    e2e_loop(max(2, min(args.warmup, 3)))
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    last_loss = e2e_loop(args.steps)
+    ev2[1].record()
+    barrier()
+    ms_e2e = D.max_over_ranks(ev2[0].elapsed_time(ev2[1]), dev)
+    _lib.PROFILE_HOOK = None
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    samples = args.steps * B * world
+    value = samples / (ms_total / 1e3)
+    e2e_value = samples / (ms_e2e / 1e3)
+    # dominant kernel family by device time inside the timed region
+    dom = max(fam.items(), key=lambda kv: kv[1]["ms"]) if fam else ("none", dict(ms=0, flops=0, launches=1))
+    gemm = fam.get("gemm_tcgen05")
+    roof = None
+    if gemm and gemm["ms"] > 0:
+        achieved = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
+        roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM family: qkv/proj/fc1/fc2/patch-embed/head fwd, dgrad, wgrad)",
+                "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tf_sust"], 4), "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+                "traffic": None, "launches_per_step": gemm["launches"] / args.steps / 1.0,
+                "avg_launch_ms": round(gemm["ms"] / gemm["launches"], 4), "flops_per_launch": gemm["flops"] / gemm["launches"],
+                "share_of_step": round(gemm["ms"] / ms_total, 4)}
+    families = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps}
+                for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_samples_per_s(budget_s=60.0)
+
+    out = {
+        "metric": "samples/s (fwd+bwd) 73ch 721x1440 SwinV2-d12", "value": round(value, 4), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode != "fp32" else "f32",
+        "data": "synthetic N(0,1) 73x721x1440 fields cropped [:720]; random-init weights (norm1/2.weight ~ N(1,0.1))",
+        "config": {"workload": "swin_73var_geo_depth12: zero_grad + forward + 'squared geometric l2' loss + backward, "
+                               f"batch {B}/GPU, C=768, 8 heads, window 9x18, 64,800 tokens/sample",
+                   "global_batch": B * world, "parallelism": f"dp{world}", "compute_mode": args.mode,
+                   "l2_policy": "per-step working set (>= 19 GB of activations) is far larger than the 126 MB L2",
+                   "attention_backend": "tcgen05" if ops_attn_is_tc(args.mode) else "cuda-core"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "kernel_families": families,
+        "model_tflops": round(value * FLOPS_FWD_BWD / 1e12 / world, 1),
+        "model_frac_of_sustained_peak": round(value * FLOPS_FWD_BWD / 1e12 / world / peaks["tf_sust"], 4),
+        "peak_mem_gib": round(peak_mem, 2),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def ops_attn_is_tc(mode_name):
+    from swin_v2_weather_b200 import ops
+    return ops.MODES[mode_name].attn_backend == 1
+
+
+# ==============================================================================================================
+# reference arm / cpu baseline: the reference algorithm (oracle port) on the host CPU cores
+# ==============================================================================================================
+def _oracle_pass(depth, threads):
+    """One fwd + loss + bwd of the oracle at full resolution with `depth` blocks; returns seconds."""
+    from oracle import swinv2_oracle as O
+    cfg = O.SwinConfig(**{**CFG, "depth": depth, "drop_path_rate": 0.0})
+    sd = O.init_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous()
+    t = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous()
+    chw = torch.ones(73) / 73
+    t0 = time.perf_counter()
+    O.loss_and_grads(x, t, sd, cfg, chw, relative=True)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_samples_per_s(budget_s=60.0):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t1 = _oracle_pass(1, threads)
+    t2 = _oracle_pass(2, threads) if t1 < budget_s else None
+    if t2 is not None:
+        per_block = max(t2 - t1, 1e-3)
+        t12 = t1 + 11 * per_block
+        sample = (f"oracle fp32 fwd+loss+bwd at full 73x720x1440 resolution with depth 1 ({t1:.1f} s) and depth 2 ({t2:.1f} s), "
+                  f"extrapolated linearly to depth 12 ({t12:.1f} s)")
+    else:
+        t12 = t1 * 12
+        sample = f"oracle fp32 fwd+loss+bwd at depth 1 ({t1:.1f} s) scaled x12"
+    return {"value": round(1.0 / t12, 5), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    # calibration (untimed): per-block cost = t(depth 2) - t(depth 1)
+    t1c = _oracle_pass(1, threads)
+    t2c = _oracle_pass(2, threads)
+    per_block = max(t2c - t1c, 1e-3)
+    budget = 240.0
+    done_w = 0
+    t_start = time.perf_counter()
+    for _ in range(args.warmup):
+        if time.perf_counter() - t_start > budget / 4:
+            break
+        _oracle_pass(1, threads)
+        done_w += 1
+    times = []
+    for _ in range(args.steps):
+        if times and time.perf_counter() - t_start > budget:
+            break
+        times.append(_oracle_pass(1, threads))
+    t1 = sum(times) / len(times)
+    t12 = t1 + 11 * per_block
+    value = 1.0 / t12
+    sample = (f"each step = oracle (port of the reference algorithm, torch fp32 CPU) fwd+loss+bwd at full 73x720x1440 resolution, "
+              f"depth 1 ({t1:.1f} s avg over {len(times)} steps); per-block cost {per_block:.1f} s calibrated once from a depth-2 "
+              f"pass; value = 1 / (t_depth1 + 11 * t_block) = depth-12 extrapolation ({t12:.1f} s/sample)")
+    out = {"impl": "reference", "metric": "samples/s (fwd+bwd) 73ch 721x1440 SwinV2-d12", "value": round(value, 5),
+           "unit": "samples/s", "n_gpus": args.gpus, "steps": len(times), "warmup": done_w, "ms_per_step": round(t12 * 1e3, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "swin_73var_geo_depth12 fwd+loss+bwd, batch 1, host CPU", "global_batch": 1, "parallelism": "cpu"},
+           "cpu_baseline": {"value": round(value, 5), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 5), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", help="compute mode: bf16 | bf16_simt | fp32")
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

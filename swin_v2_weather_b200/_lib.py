@@ -68,9 +68,21 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+# kernels launched per C-ABI call (everything else launches exactly one); used for the launch counter
+_KERNELS_PER_CALL = {"swinb200_latw_l2_fwd": 2}
+LAUNCH_COUNT = 0          # our kernels launched so far in this process
+PROFILE_HOOK = None       # optional callable(name, args) -> context manager; set by bench.py to time kernels
+
+
 def call(name: str, *args) -> None:
+    global LAUNCH_COUNT
     lib = load()
-    rc = getattr(lib, name)(*args)
+    LAUNCH_COUNT += _KERNELS_PER_CALL.get(name, 1)
+    if PROFILE_HOOK is not None:
+        with PROFILE_HOOK(name, args):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.swinb200_last_error().decode("utf-8", "replace")
         raise SwinB200Error(f"{name} failed (code {rc}): {msg}")
