@@ -6,6 +6,7 @@ activation storage + fp32 row statistics -- ~24.6 KB/token, 1.6 GB per block per
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -17,10 +18,12 @@ from .ops import ComputeMode, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, E
 # ---- bf16 weight shadows ------------------------------------------------------------------------------
 class _ShadowCache:
     """bf16 copies of fp32 master weights, refreshed when the parameter's version counter moves
-    (optimizer.step() bumps it).  Parameters themselves are never replaced (optimizer / DDP hold them)."""
+    (optimizer.step() bumps it).  Parameters themselves are never replaced (optimizer / DDP hold them).
+    Entries are validated by object identity (weak reference), version and storage pointer: `id()` values and
+    allocator blocks are both recycled once a model is freed, so neither alone identifies a parameter."""
 
     def __init__(self):
-        self._store: Dict[int, Tuple[int, int, torch.Tensor]] = {}
+        self._store: Dict[int, Tuple[weakref.ref, int, int, torch.Tensor]] = {}
 
     def get(self, w: torch.Tensor, mode: ComputeMode) -> torch.Tensor:
         if mode.act_dtype == torch.float32:
@@ -28,11 +31,13 @@ class _ShadowCache:
         key = id(w)
         ent = self._store.get(key)
         ver, ptr = w._version, w.data_ptr()
-        if ent is not None and ent[0] == ver and ent[1] == ptr:
-            return ent[2]
-        out = ent[2] if (ent is not None and ent[2].shape == w.shape and ent[2].device == w.device) else None
-        sh = ops.cast_bf16(w.detach().contiguous(), out)
-        self._store[key] = (ver, ptr, sh)
+        if ent is not None and ent[0]() is w and ent[1] == ver and ent[2] == ptr and ent[3].shape == w.shape:
+            return ent[3]
+        reuse = ent is not None and ent[0]() is w and ent[3].shape == w.shape and ent[3].device == w.device
+        sh = ops.cast_bf16(w.detach().contiguous(), ent[3] if reuse else None)
+        if len(self._store) > 4096:
+            self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
+        self._store[key] = (weakref.ref(w), ver, ptr, sh)
         return sh
 
     def clear(self):
