@@ -188,6 +188,16 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    if args.profile_step:
+        # one warmed-up step bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off`
+        step(x_res, t_res)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(x_res, t_res)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
+
     timer = KernelTimer()
     _lib.PROFILE_HOOK = timer.hook
 
@@ -397,6 +407,7 @@ def main():
     ap.add_argument("--mode", default="bf16", help="compute mode: bf16 | bf16_simt | fp32")
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

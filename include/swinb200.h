@@ -134,6 +134,14 @@ int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, co
                          const float* num, const float* den, const float* gloss, int relative, int squared,
                          float* dprd, int B, int C, int H, int W, void* stream);
 
+/* ---- bring-up / test hook ------------------------------------------------------------------------------
+ * D[128,N] (fp32) = A[128,K] * B[N,K]^T through one tcgen05.mma chain using the un-swizzled core-matrix
+ * shared-memory layout of the attention kernels.  a_mode: 0 = A (128,K) from smem K-major, 1 = A stored (K,128)
+ * from smem M-major, 2 = A (128,K) from tensor memory;  b_mode: 0 = B stored (N,K), 1 = B stored (K,N).
+ * pad16: extra 16-byte units added to the chunk stride.  No reference counterpart. */
+int swinb200_debug_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mode, int b_mode,
+                              int pad16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,17 +1,662 @@
-// tcgen05 windowed cosine attention (placeholder until the kernel lands; reports UNSUPPORTED loudly).
+// tcgen05 windowed cosine attention for sm_100a (bf16 storage, fp32 accumulation in tensor memory).
+//
+// One CTA per (sample, window, head).  The cyclic shift, window partition and window reverse of the reference
+// (swinv2_global.py:89-119, 446-478) are folded into the gather / scatter addressing: slot n = a*Ww + c of window
+// (wh, ww) is token ((wh*Wh + a + s0) % H, (ww*Ww + c + s1) % W), so no rolled or permuted copy ever reaches HBM.
+//
+// Shared-memory operand layout (un-swizzled UMMA core matrices), for a [rows x cols] bf16 tile:
+//     byte(row, col) = (col / 8) * chunk_stride + row * 16 + (col % 8) * 2
+// i.e. "[16-byte column chunk][row][8 elements]".  One 16-byte cp.async (or st.shared) per (row, chunk); consecutive
+// rows are consecutive 16-byte words -> conflict-free stores.  The same bytes serve as a K-major operand
+// (rows = m/n, cols = k: LBO = chunk_stride, SBO = 128) and as an MN-major operand (rows = k, cols = m/n:
+// LBO = 128, SBO = chunk_stride), which is what lets K^ feed S = Q^ K^T and dQ = dS K^ without a transpose.
+//
+// forward:   S = Q^ K^T (tcgen05, TMEM) -> thread-per-row softmax(scale*S + bias + mask) -> P (bf16, smem)
+//            -> O = P V (tcgen05, accumulator aliases S) -> O / rowsum -> scatter to (T, C); row LSE saved.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace swinb200 {
+using namespace ptx;
 
-int attn_tcgen05_fwd(const void*, const float*, const float*, void*, float*, int, int, int, int, int, int, int, int, int,
-                     cudaStream_t) {
-  set_error("window_attn_fwd: the tcgen05 back end is not built in this version");
-  return SWINB200_ERR_UNSUPPORTED;
+constexpr int kMaxLP = 176;  // padded keys per window (multiple of 16); 9x18 = 162 -> 176
+
+__host__ __device__ constexpr uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-int attn_tcgen05_bwd(const void*, const float*, const float*, const float*, const void*, const void*, const float*, void*,
-                     float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t) {
-  set_error("window_attn_bwd: the tcgen05 back end is not built in this version");
-  return SWINB200_ERR_UNSUPPORTED;
+
+struct AttnGeom {
+  int B, H, W, C, heads, Wh, Ww, s0, s1;
+  int L, LP, nW, nWw;
+};
+
+__device__ __forceinline__ int win_token(const AttnGeom& g, int b, int w, int n, int& rolled_row) {
+  const int wh = w / g.nWw, ww = w - wh * g.nWw;
+  const int a = n / g.Ww, c = n - a * g.Ww;
+  rolled_row = wh * g.Wh + a;
+  int i = rolled_row + g.s0;
+  if (i >= g.H) i -= g.H;
+  int j = ww * g.Ww + c + g.s1;
+  if (j >= g.W) j -= g.W;
+  return (b * g.H + i) * g.W + j;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+struct FwdSmem {
+  static constexpr int kChunks = D / 8;
+  static constexpr int kCS = kMaxLP * 16 + 16;                  // chunk stride of the Q / K / V tiles (bank de-phasing pad)
+  static constexpr int kTile = kChunks * kCS;                   // one operand
+  static constexpr int kPCS = 128 * 16;                         // chunk stride of a P tile (128 query rows)
+  static constexpr int kPTile = (kMaxLP / 8) * kPCS;            // 22 key chunks
+  static constexpr int kOffQ = 0, kOffK = kTile, kOffV = 2 * kTile, kOffP = 3 * kTile;   // Q first: its M-tile over-read lands in K/V
+  static constexpr int kOffTok = kOffP + 2 * kPTile;
+  static constexpr int kOffBar = kOffTok + kMaxLP * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256, 1)
+attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ scale_p, const float* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const AttnGeom g) {
+  using SM = FwdSmem<D>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sQ = smem + SM::kOffQ;
+  unsigned char* sK = smem + SM::kOffK;
+  unsigned char* sV = smem + SM::kOffV;
+  unsigned char* sP = smem + SM::kOffP;
+  int* tok = reinterpret_cast<int*>(smem + SM::kOffTok);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);   // [0] S ready, [1] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.x % g.heads;
+  const int w = (blockIdx.x / g.heads) % g.nW;
+  const int b = blockIdx.x / (g.heads * g.nW);
+  const int L = g.L, LP = g.LP;
+  const int ntiles = (L > 128) ? 2 : 1;
+  const bool shifted = (g.s0 > 0) || (g.s1 > 0);
+
+  // ---- prologue: token table, barriers, tensor memory ---------------------------------------------------------
+  int label_split = LP;   // first slot whose region label is 1 (keys >= label_split are "label 1")
+  if (shifted) {
+    // label(n) = (rolled_row >= H - s0) with rolled_row = wh*Wh + n / Ww  (every row if only the W shift is active)
+    const int wh = w / g.nWw;
+    if (g.s0 > 0) {
+      const int first_row = g.H - g.s0 - wh * g.Wh;     // window-local row where label 1 starts
+      label_split = first_row <= 0 ? 0 : (first_row >= g.Wh ? LP : first_row * g.Ww);
+    } else {
+      label_split = 0;
+    }
+  }
+  for (int n = tid; n < LP; n += 256) {
+    int rr;
+    tok[n] = (n < L) ? win_token(g, b, w, n, rr) : -1;
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // zero the pad rows [L, LP) of Q, K and V (V pad rows must be finite: P is exactly 0 there)
+  for (int i = tid; i < (LP - L) * SM::kChunks * 3; i += 256) {
+    const int op = i / ((LP - L) * SM::kChunks);
+    const int rem = i - op * (LP - L) * SM::kChunks;
+    const int c = rem / (LP - L), r = L + rem % (LP - L);
+    *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  // ---- gather Q^, K^, V of this (window, head): one 16-byte cp.async per (token, 8 channels) ----------------------
+  {
+    const int C3 = 3 * g.C;
+    const int per_op = L * SM::kChunks;
+    for (int i = tid; i < 3 * per_op; i += 256) {
+      const int op = i / per_op;
+      const int rem = i - op * per_op;
+      const int n = rem / SM::kChunks, c = rem - n * SM::kChunks;
+      const __nv_bfloat16* src = qkv + (size_t)tok[n] * C3 + op * g.C + head * D + c * 8;
+      cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
+    }
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- S_t = Q^_t K^T ----------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, LP, false, false);
+    const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+    for (int t = 0; t < ntiles; ++t)
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16_ss(tmem_base + t * kMaxLP, umma_desc_nosw(q0 + 2 * k * SM::kCS + t * 128 * 16, SM::kCS, 128),
+                     umma_desc_nosw(k0 + 2 * k * SM::kCS, SM::kCS, 128), idesc, k > 0);
+    umma_commit(&bars[0]);
+  }
+
+  // ---- softmax: thread = one query row of tile t ---------------------------------------------------------------------
+  const int t = warp >> 2;                       // warpgroup -> query tile
+  const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
+  const int n = t * 128 + r;                     // slot (query) index inside the window
+  const bool row_ok = (t < ntiles) && (n < L);
+  const float scale_l2 = scale_p[head] * 1.4426950408889634f;   // work in the log2 domain
+  const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+  const int my_label = (n >= label_split) ? 1 : 0;
+  const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * kMaxLP);
+  float row_sum = 0.f, row_max = -INFINITY;
+
+  mbar_wait(&bars[0], 0, 500);
+  tc_fence_after();
+  if (t < ntiles) {
+    // pass 1: row maximum of the (log2-domain) logits
+    for (int c0 = 0; c0 < LP; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(t_s + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int key = c0 + j;
+        float s = __uint_as_float(v[j]) * scale_l2;
+        if (brow != nullptr && key < L) s += brow[key] * 1.4426950408889634f;
+        if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * 1.4426950408889634f;
+        if (key < L) row_max = fmaxf(row_max, s);
+      }
+    }
+    // pass 2: p = 2^(s - max), row sum, bf16 P tile
+    unsigned char* myP = sP + t * SM::kPTile + r * 16;
+    for (int c0 = 0; c0 < LP; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(t_s + c0, v);
+      tmem_ld_wait();
+      float p[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int key = c0 + j;
+        float s = __uint_as_float(v[j]) * scale_l2;
+        if (brow != nullptr && key < L) s += brow[key] * 1.4426950408889634f;
+        if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * 1.4426950408889634f;
+        const float e = (key < L && row_ok) ? exp2f(s - row_max) : 0.f;
+        // the probabilities that multiply V are the bf16-rounded ones; normalise by their sum
+        p[j] = __bfloat162float(__float2bfloat16_rn(e));
+        row_sum += p[j];
+      }
+      uint4 lo, hi;
+      lo.x = pack_bf16x2(p[0], p[1]);  lo.y = pack_bf16x2(p[2], p[3]);  lo.z = pack_bf16x2(p[4], p[5]);  lo.w = pack_bf16x2(p[6], p[7]);
+      hi.x = pack_bf16x2(p[8], p[9]);  hi.y = pack_bf16x2(p[10], p[11]); hi.z = pack_bf16x2(p[12], p[13]); hi.w = pack_bf16x2(p[14], p[15]);
+      *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = lo;
+      *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = hi;
+    }
+    if (row_ok)
+      lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] = (row_max + log2f(row_sum)) * 0.6931471805599453f;
+  }
+  fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+  tc_fence_before();
+  __syncthreads();            // every thread has finished reading S: O may overwrite its columns
+
+  // ---- O_t = P_t V  (accumulator aliases S_t) ----------------------------------------------------------------------------
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, D, false, true);
+    const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sV);
+    for (int tt = 0; tt < ntiles; ++tt)
+      for (int k = 0; k < LP / 16; ++k)
+        umma_bf16_ss(tmem_base + tt * kMaxLP, umma_desc_nosw(p0 + tt * SM::kPTile + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(v0 + k * 256, 128, SM::kCS), idesc, k > 0);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0, 501);
+  tc_fence_after();
+  if (t < ntiles) {
+    const float inv = row_ok ? 1.0f / row_sum : 0.f;
+    __nv_bfloat16* orow = row_ok ? o + (size_t)tok[n] * g.C + head * D : nullptr;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(t_s + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        float a8[8], b8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a8[j] = __uint_as_float(v[j]) * inv;
+          b8[j] = __uint_as_float(v[8 + j]) * inv;
+        }
+        st8(orow + c0, a8);
+        st8(orow + c0 + 8, b8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
+  g.B = B; g.H = H; g.W = W; g.C = C; g.heads = heads; g.Wh = Wh; g.Ww = Ww; g.s0 = s0; g.s1 = s1;
+  g.L = Wh * Ww;
+  g.LP = (g.L + 15) / 16 * 16;
+  g.nWw = W / Ww;
+  g.nW = (H / Wh) * g.nWw;
+  if (g.LP > kMaxLP) {
+    set_error("window_attn (tcgen05): window %dx%d has %d tokens; this kernel handles up to %d", Wh, Ww, g.L, kMaxLP);
+    return SWINB200_ERR_UNSUPPORTED;
+  }
+  if (g.LP < 16 || C / heads != 96) {
+    set_error("window_attn (tcgen05): head_dim %d is not instantiated (96 only)", C / heads);
+    return SWINB200_ERR_UNSUPPORTED;
+  }
+  return SWINB200_OK;
+}
+
+int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, void* o, float* lse, int B, int H, int W, int C,
+                     int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
+  AttnGeom g;
+  if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
+  using SM = FwdSmem<96>;
+  static bool configured = false;
+  if (!configured) {
+    SWB_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  attn_tc_fwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>((const __nv_bfloat16*)qkv, scale, bias, (__nv_bfloat16*)o,
+                                                                        lse, g);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+// Two sweeps over the same resident operands (Q^, K^, V, dO in shared memory):
+//   A (query-major, per 128-query tile):  S = Q^ K^T, dP = dO V^T  ->  dS = P o (dP - D)  ->  dQ^ = dS K^  -> dq
+//   B (key-major,   per 128-key tile):    S^T = K^ Q^T, dP^T = V dO^T -> P^T, dS^T -> dV = P^T dO, dK^ = dS^T Q^ -> dk
+// S and dP are recomputed for the transposed sweep instead of transposing P / dS through shared memory; the tensor
+// pipe has the headroom (the kernel is bound by the softmax arithmetic and HBM, not by the MMAs).
+template <int D>
+struct BwdSmem {
+  static constexpr int kChunks = D / 8;
+  static constexpr int kCS = kMaxLP * 16 + 16;
+  static constexpr int kTile = kChunks * kCS;
+  static constexpr int kPCS = 128 * 16;
+  static constexpr int kPTile = (kMaxLP / 8) * kPCS;
+  static constexpr int kOffQ = 0, kOffK = kTile, kOffV = 2 * kTile, kOffG = 3 * kTile;   // G = dO
+  static constexpr int kOffP = 4 * kTile, kOffDS = kOffP + kPTile;
+  static constexpr int kOffTok = kOffDS + kPTile;
+  static constexpr int kOffLse = kOffTok + kMaxLP * 4;
+  static constexpr int kOffDv = kOffLse + kMaxLP * 4;
+  static constexpr int kOffRed = kOffDv + kMaxLP * 4;
+  static constexpr int kOffBar = kOffRed + 64;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256, 1)
+attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ inv_norm, const float* __restrict__ scale_p,
+                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dscale,
+                   float* __restrict__ dbias, const AttnGeom g) {
+  using SM = BwdSmem<D>;
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sQ = smem + SM::kOffQ;
+  unsigned char* sK = smem + SM::kOffK;
+  unsigned char* sV = smem + SM::kOffV;
+  unsigned char* sG = smem + SM::kOffG;
+  unsigned char* sP = smem + SM::kOffP;
+  unsigned char* sDS = smem + SM::kOffDS;
+  int* tok = reinterpret_cast<int*>(smem + SM::kOffTok);
+  float* lse2 = reinterpret_cast<float*>(smem + SM::kOffLse);   // log2-domain LSE per query (+inf for pad queries)
+  float* Dv = reinterpret_cast<float*>(smem + SM::kOffDv);      // rowsum(dO o O) per query
+  float* red = reinterpret_cast<float*>(smem + SM::kOffRed);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.x % g.heads;
+  const int w = (blockIdx.x / g.heads) % g.nW;
+  const int b = blockIdx.x / (g.heads * g.nW);
+  const int L = g.L, LP = g.LP, C = g.C, C3 = 3 * g.C;
+  const int ntiles = (L > 128) ? 2 : 1;
+  const bool shifted = (g.s0 > 0) || (g.s1 > 0);
+  int label_split = LP;
+  if (shifted) {
+    const int wh = w / g.nWw;
+    if (g.s0 > 0) {
+      const int first_row = g.H - g.s0 - wh * g.Wh;
+      label_split = first_row <= 0 ? 0 : (first_row >= g.Wh ? LP : first_row * g.Ww);
+    } else {
+      label_split = 0;
+    }
+  }
+
+  // ---- prologue --------------------------------------------------------------------------------------------------
+  for (int n = tid; n < LP; n += 256) {
+    int rr;
+    tok[n] = (n < L) ? win_token(g, b, w, n, rr) : -1;
+    lse2[n] = (n < L) ? lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] * kLog2e : INFINITY;
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < (LP - L) * SM::kChunks * 4; i += 256) {      // zero pad rows [L, LP) of Q^, K^, V, dO
+    const int op = i / ((LP - L) * SM::kChunks);
+    const int rem = i - op * (LP - L) * SM::kChunks;
+    const int c = rem / (LP - L), r = L + rem % (LP - L);
+    *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  {
+    const int per_op = L * SM::kChunks;
+    for (int i = tid; i < 4 * per_op; i += 256) {
+      const int op = i / per_op;
+      const int rem = i - op * per_op;
+      const int n = rem / SM::kChunks, c = rem - n * SM::kChunks;
+      const __nv_bfloat16* src = (op < 3) ? qkv + (size_t)tok[n] * C3 + op * C + head * D + c * 8
+                                          : d_o + (size_t)tok[n] * C + head * D + c * 8;
+      cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
+    }
+    // D_n = <dO_n, O_n> while the copies are in flight
+    for (int n = tid; n < LP; n += 256) {
+      float acc = 0.f;
+      if (n < L) {
+        const __nv_bfloat16* go = d_o + (size_t)tok[n] * C + head * D;
+        const __nv_bfloat16* oo = o + (size_t)tok[n] * C + head * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+          float a8[8], b8[8];
+          ld8(go + c, a8);
+          ld8(oo + c, b8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(a8[e], b8[e], acc);
+        }
+      }
+      Dv[n] = acc;
+    }
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), g0 = smem_u32(sG), p0 = smem_u32(sP), ds0 = smem_u32(sDS);
+  const uint32_t idesc_s = umma_idesc_bf16(128, LP, false, false);      // [128 x LP] = A(k-major) * B(k-major)^T
+  const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);        // [128 x D]  = A(k-major) * B(n-major)
+  const float scale = scale_p[head];
+  const float scale_l2 = scale * kLog2e;
+  uint32_t parity = 0;
+
+  const int r = (warp & 3) * 32 + lane;                 // row inside the current 128-row tile == TMEM lane
+  const int half = warp >> 2;                           // which half of the LP columns this thread handles
+  const int c_begin = half * (LP / 2), c_end = c_begin + LP / 2;    // LP/2 is a multiple of 8
+  const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  float dsc_acc = 0.f;
+
+  // ================================ sweep A: query-major -> dq ================================
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // S = Q^_t K^T
+        umma_bf16_ss(tmem_base, umma_desc_nosw(q0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
+                     umma_desc_nosw(k0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // dP = dO_t V^T
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(g0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
+                     umma_desc_nosw(v0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 600 + t);
+    parity ^= 1;
+    tc_fence_after();
+    {
+      const int n = t * 128 + r;                        // query slot of this thread
+      const bool row_ok = n < L;
+      const float my_lse = lse2[min(n, LP - 1)];
+      const float my_D = Dv[min(n, LP - 1)];
+      const int my_label = (n >= label_split) ? 1 : 0;
+      const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+      float* dbrow = (dbias != nullptr && row_ok) ? dbias + ((size_t)head * L + n) * L : nullptr;
+      for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+        uint32_t sv[8], pv[8];
+        tmem_ld_32x8(t_lane + c0, sv);
+        tmem_ld_32x8(t_lane + kMaxLP + c0, pv);
+        tmem_ld_wait();
+        float ds[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = c0 + j;
+          const float cosv = __uint_as_float(sv[j]);
+          float s = cosv * scale_l2;
+          if (brow != nullptr && key < L) s += brow[key] * kLog2e;
+          if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
+          const float p = (key < L && row_ok) ? exp2f(s - my_lse) : 0.f;
+          // pad rows / pad keys read whatever follows the real rows in shared memory: keep them exactly zero
+          ds[j] = (key < L && row_ok) ? p * (__uint_as_float(pv[j]) - my_D) : 0.f;
+          if (key < L && row_ok) dsc_acc = fmaf(ds[j], cosv, dsc_acc);
+          if (dbrow != nullptr && key < L) atomicAdd(dbrow + key, ds[j]);
+        }
+        uint4 pk;
+        pk.x = pack_bf16x2(ds[0], ds[1]); pk.y = pack_bf16x2(ds[2], ds[3]); pk.z = pack_bf16x2(ds[4], ds[5]); pk.w = pack_bf16x2(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(sDS + (c0 / 8) * SM::kPCS + r * 16) = pk;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < LP / 16; ++k)     // dQ^_t = dS K^   (K^ read n-major: rows = keys = k-dimension)
+        umma_bf16_ss(tmem_base, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(k0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 610 + t);
+    parity ^= 1;
+    tc_fence_after();
+    if (half == 0) {
+      // dq = inv_norm * (dq^ - q^ <q^, dq^>),  dq^ = scale * (dS K^)
+      const int n = t * 128 + r;
+      const bool row_ok = n < L;
+      float dq[D];
+      float dot = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_lane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dq[c0 + j] = __uint_as_float(v[j]) * scale;
+      }
+      if (row_ok) {
+        float qh[D];
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+          float t8[8];
+          ld8(reinterpret_cast<const __nv_bfloat16*>(sQ + c * SM::kCS + n * 16), t8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            qh[c * 8 + e] = t8[e];
+            dot = fmaf(t8[e], dq[c * 8 + e], dot);
+          }
+        }
+        const float inq = inv_norm[(size_t)tok[n] * 2 * g.heads + head];
+        __nv_bfloat16* dst = dqkv + (size_t)tok[n] * C3 + head * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 8) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o8[e] = inq * (dq[c + e] - qh[c + e] * dot);
+          st8(dst + c, o8);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // dQ^ has been read: the next tile's S may overwrite it
+  }
+
+  // ================================ sweep B: key-major -> dk, dv ================================
+  for (int u = 0; u < ntiles; ++u) {
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // S^T = K^_u Q^T
+        umma_bf16_ss(tmem_base, umma_desc_nosw(k0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
+                     umma_desc_nosw(q0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // dP^T = V_u dO^T
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(v0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
+                     umma_desc_nosw(g0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 620 + u);
+    parity ^= 1;
+    tc_fence_after();
+    {
+      const int jk = u * 128 + r;                       // key slot of this thread
+      const bool key_ok = jk < L;
+      const int key_label = (jk >= label_split) ? 1 : 0;
+      for (int c0 = c_begin; c0 < c_end; c0 += 8) {     // columns = queries
+        uint32_t sv[8], pv[8];
+        tmem_ld_32x8(t_lane + c0, sv);
+        tmem_ld_32x8(t_lane + kMaxLP + c0, pv);
+        tmem_ld_wait();
+        float pp[8], ds[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int qi = c0 + j;
+          float s = __uint_as_float(sv[j]) * scale_l2;
+          if (bias != nullptr && key_ok && qi < L) s += bias[((size_t)head * L + qi) * L + jk] * kLog2e;
+          if (shifted && ((qi >= label_split) ? 1 : 0) != key_label) s += -100.0f * kLog2e;
+          const float p = key_ok ? exp2f(s - lse2[qi]) : 0.f;      // lse2 = +inf for pad queries -> p = 0
+          pp[j] = p;
+          ds[j] = (key_ok && qi < L) ? p * (__uint_as_float(pv[j]) - Dv[qi]) : 0.f;
+        }
+        uint4 pk, dk;
+        pk.x = pack_bf16x2(pp[0], pp[1]); pk.y = pack_bf16x2(pp[2], pp[3]); pk.z = pack_bf16x2(pp[4], pp[5]); pk.w = pack_bf16x2(pp[6], pp[7]);
+        dk.x = pack_bf16x2(ds[0], ds[1]); dk.y = pack_bf16x2(ds[2], ds[3]); dk.z = pack_bf16x2(ds[4], ds[5]); dk.w = pack_bf16x2(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(sP + (c0 / 8) * SM::kPCS + r * 16) = pk;
+        *reinterpret_cast<uint4*>(sDS + (c0 / 8) * SM::kPCS + r * 16) = dk;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < LP / 16; ++k)     // dV_u = P^T dO   (dO read n-major: rows = queries = k-dimension)
+        umma_bf16_ss(tmem_base, umma_desc_nosw(p0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(g0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      for (int k = 0; k < LP / 16; ++k)     // dK^_u = dS^T Q^
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(q0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 630 + u);
+    parity ^= 1;
+    tc_fence_after();
+    {
+      const int jk = u * 128 + r;
+      const bool key_ok = jk < L;
+      float acc[D];
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_lane + half * kMaxLP + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
+      }
+      if (key_ok) {
+        if (half == 0) {                                 // dv
+          __nv_bfloat16* dst = dqkv + (size_t)tok[jk] * C3 + 2 * C + head * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = acc[c + e];
+            st8(dst + c, o8);
+          }
+        } else {                                         // dk = inv_norm * (dk^ - k^ <k^, dk^>)
+          float kh[D];
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < D / 8; ++c) {
+            float t8[8];
+            ld8(reinterpret_cast<const __nv_bfloat16*>(sK + c * SM::kCS + jk * 16), t8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              kh[c * 8 + e] = t8[e];
+              acc[c * 8 + e] *= scale;
+              dot = fmaf(t8[e], acc[c * 8 + e], dot);
+            }
+          }
+          const float ink = inv_norm[(size_t)tok[jk] * 2 * g.heads + g.heads + head];
+          __nv_bfloat16* dst = dqkv + (size_t)tok[jk] * C3 + C + head * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = ink * (acc[c + e] - kh[c + e] * dot);
+            st8(dst + c, o8);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- d(scale) = sum dS o cos -----------------------------------------------------------------------------------------
+  dsc_acc = warp_sum(dsc_acc);
+  if (lane == 0) red[warp] = dsc_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(dscale + head, s);
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale, const float* bias, const void* o,
+                     const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W, int C,
+                     int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
+  AttnGeom g;
+  if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
+  using SM = BwdSmem<96>;
+  static bool configured = false;
+  if (!configured) {
+    SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  attn_tc_bwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>(
+      (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
+      (__nv_bfloat16*)dqkv, dscale, dbias, g);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
 }
 
 }  // namespace swinb200

@@ -36,7 +36,7 @@ class ComputeMode:
         return BF16 if self.act_dtype == torch.bfloat16 else F32
 
 
-MODE_BF16 = ComputeMode("bf16", torch.bfloat16, BACKEND_TCGEN05, BACKEND_SIMT)
+MODE_BF16 = ComputeMode("bf16", torch.bfloat16, BACKEND_TCGEN05, BACKEND_TCGEN05)
 MODE_BF16_SIMT = ComputeMode("bf16_simt", torch.bfloat16, BACKEND_SIMT, BACKEND_SIMT)
 MODE_FP32 = ComputeMode("fp32", torch.float32, BACKEND_SIMT, BACKEND_SIMT)
 MODES = {m.name: m for m in (MODE_BF16, MODE_BF16_SIMT, MODE_FP32)}
@@ -197,12 +197,23 @@ def shift_mask(H, W, Wh, Ww, s0, s1, device) -> torch.Tensor:
     return mask
 
 
+def attn_backend_for(mode: ComputeMode, C: int, heads: int, Wh: int, Ww: int) -> int:
+    """The tcgen05 attention kernels are instantiated for head_dim 96 and windows of up to 176 (padded) tokens --
+    every shipped config (9x18 = 162).  Other geometries run on the CUDA-core kernels; this is a dispatch on the
+    problem shape decided up front, not an error fallback."""
+    if mode.attn_backend == BACKEND_TCGEN05 and C // heads == 96 and (Wh * Ww + 15) // 16 * 16 <= 176:
+        return BACKEND_TCGEN05
+    return BACKEND_SIMT
+
+
 def window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, Wh, Ww, s0, s1, mode: ComputeMode, backend=None):
     T = B * H * W
+    if backend is None:
+        backend = attn_backend_for(mode, C, heads, Wh, Ww)
     nW, L = (H // Wh) * (W // Ww), Wh * Ww
     o = torch.empty((T, C), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((B, nW, heads, L), dtype=torch.float32, device=qkv.device)
-    _lib.call("swinb200_window_attn_fwd", mode.attn_backend if backend is None else backend, _chk(qkv, "qkv"), _code(qkv.dtype),
+    _lib.call("swinb200_window_attn_fwd", backend, _chk(qkv, "qkv"), _code(qkv.dtype),
               _chk(scale, "scale", torch.float32), _chk(bias, "bias", torch.float32, True), o.data_ptr(), lse.data_ptr(),
               B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
     return o, lse
@@ -211,10 +222,12 @@ def window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, Wh, Ww, s0, s1, mode: C
 def window_attn_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, B, H, W, C, heads, Wh, Ww, s0, s1, mode: ComputeMode,
                     backend=None):
     L = Wh * Ww
+    if backend is None:
+        backend = attn_backend_for(mode, C, heads, Wh, Ww)
     dqkv = torch.empty_like(qkv)
     dscale = torch.zeros((heads,), dtype=torch.float32, device=qkv.device)
     dbias = torch.zeros((heads, L, L), dtype=torch.float32, device=qkv.device) if bias is not None else None
-    _lib.call("swinb200_window_attn_bwd", mode.attn_backend if backend is None else backend, _chk(qkv, "qkv"), _code(qkv.dtype),
+    _lib.call("swinb200_window_attn_bwd", backend, _chk(qkv, "qkv"), _code(qkv.dtype),
               _chk(inv_norm, "inv_norm", torch.float32), _chk(scale, "scale", torch.float32),
               _chk(bias, "bias", torch.float32, True), _chk(o, "o", qkv.dtype), _chk(d_o, "d_o", qkv.dtype),
               _chk(lse, "lse", torch.float32), dqkv.data_ptr(), dscale.data_ptr(), 0 if dbias is None else dbias.data_ptr(),

@@ -1,0 +1,5 @@
+#!/bin/bash
+# generic trip: run GPU tests (selection via $1), keep logs
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -q --timeout 600 $1 > gpurun_out/t_all.log 2>&1; echo "tests exit $?"
+grep -E "^E  |^FAILED|passed|failed" gpurun_out/t_all.log | cut -c1-400 | tail -40
