@@ -1,12 +1,14 @@
 // tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulation in TMEM.
 //
-// Persistent, warp-specialised, one CTA per SM:
+// Persistent, warp-specialised, one CTA per SM (320 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores)
+//   warps 2..9  epilogue       (two groups of 4 warps; each group owns every other 128-byte column chunk of the tile:
+//                               tcgen05.ld -> fused epilogue in registers -> swizzled smem staging -> TMA store /
+//                               TMA reduce-add, so global writes are full 128-byte rows issued by the copy engine)
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
-// token-major, reduction over tokens, optional split-K with fp32 red.global) all run without transposed copies.
+// token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
 #include <cuda.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -17,16 +19,15 @@ using namespace ptx;
 
 constexpr int GBM = 128;  // UMMA M (cta_group::1)
 constexpr int GBK = 64;   // k per pipeline stage (one 128-byte swizzle row of bf16)
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kStagingBytes = 128 * 128;   // one [128 rows x 128 B] output chunk per epilogue group
 
 struct GemmTcParams {
   int M, N, K;
   const float* bias;
-  void* D;
-  void* D2;
   const void* aux;
-  int ldd, ld_aux;
-  int atomic_out;  // EPI_F32: 1 = red.global.add (split-K / accumulate), 0 = plain store
+  int ld_aux;
+  int atomic_out;  // EPI_F32: 1 = TMA reduce-add (split-K / accumulate), 0 = plain TMA store
   int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
 };
 
@@ -35,18 +36,61 @@ struct GemmCfg {
   static constexpr int kStageA = GBM * GBK * 2;
   static constexpr int kStageB = BN * GBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kOffStaging = kStages * kStage;
+  static constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
+  static constexpr int kSmem = kOffBars + 256 + 1024 /* alignment slack */;
 };
+
+// exact-GELU pieces from one exponential: Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 on erf), fast enough to keep the
+// epilogue under the MMA time of a K=768 tile.  Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  phi(x) = exp(-x^2/2) / sqrt(2 pi).
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& x_pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  x_pdf = x * 0.39894228040143267794f * e;
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// 16-byte chunk `c` (0..7) of staging row `r`, 128B-swizzled exactly as the TMA store expects
+__device__ __forceinline__ unsigned char* staging_chunk(unsigned char* buf, int r, int c) {
+  return buf + r * 128 + ((c ^ (r & 7)) << 4);
+}
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmTcParams p) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool kF32Out = (EPI == SWINB200_EPI_ADD_F32 || EPI == SWINB200_EPI_F32);
+  constexpr int kChunkCols = kF32Out ? 32 : 64;          // 128 bytes of output per row per chunk
+  constexpr int kNumChunks = BN / kChunkCols;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -58,13 +102,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+    if (EPI == SWINB200_EPI_BIAS_GELU) prefetch_tmap(&tmD2);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], 8);
     }
     fence_barrier_init();
   }
@@ -152,7 +198,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================================= epilogue ===================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2;               // 0..7
+    const int grp = ew >> 2;               // epilogue group: owns chunks grp, grp+2, ...
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;     // row inside the tile
+    const bool issuer = (ew & 3) == 0 && lane == 0;
+    unsigned char* stg = smem + Cfg::kOffStaging + grp * kStagingBytes;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int rest = tile / p.split_k;
@@ -162,91 +213,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t use = (uint32_t)(local >> 1);
       mbar_wait(&tfull_bar[buf], use & 1, 400 + buf);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
+      const int m = m0 + r;
       const bool row_ok = m < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + cc * 32), r);
-        tmem_ld_wait();
-        const int nb = n0 + cc * 32;
-        if (row_ok && nb < p.N) {
-          float v[32];
+      for (int ch = grp; ch < kNumChunks; ch += 2) {
+        const int nb = n0 + ch * kChunkCols;
+        if (nb >= p.N) break;                       // whole chunk beyond N (uniform across the group)
+        float v[kChunkCols];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU) {
-            if (p.bias) {
+        for (int q = 0; q < kChunkCols / 32; ++q) {
+          uint32_t rr[32];
+          tmem_ld_32x32(t_row + ch * kChunkCols + q * 32, rr);
+          tmem_ld_wait();
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (nb + g * 4 < p.N) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
-                  v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-                }
+          for (int i = 0; i < 32; ++i) v[q * 32 + i] = __uint_as_float(rr[i]);
+        }
+        if (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int g = 0; g < kChunkCols / 4; ++g)
+              if (nb + g * 4 < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
+                v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
               }
-            }
           }
-          if (EPI == SWINB200_EPI_BIAS) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (nb + g * 8 < p.N) {
-                float t8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) t8[e] = v[g * 8 + e];
-                st8(d + g * 8, t8);
-              }
-          } else if (EPI == SWINB200_EPI_BIAS_GELU) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
-            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + nb;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (nb + g * 8 < p.N) {
-                float h8[8], g8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  h8[e] = v[g * 8 + e];
-                  g8[e] = gelu_erf(Act<__nv_bfloat16>::round(h8[e]));
-                }
-                st8(d2 + g * 8, h8);
-                st8(d + g * 8, g8);
-              }
-          } else if (EPI == SWINB200_EPI_DGELU) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)m * p.ldd + nb;
+        } else if (EPI == SWINB200_EPI_DGELU) {
+          if (row_ok) {
             const __nv_bfloat16* hx = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + nb;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < kChunkCols / 8; ++g)
               if (nb + g * 8 < p.N) {
-                float h8[8], o8[8];
+                float h8[8];
                 ld8(hx + g * 8, h8);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o8[e] = v[g * 8 + e] * gelu_erf_grad(h8[e]);
-                st8(d + g * 8, o8);
+                for (int e = 0; e < 8; ++e) {
+                  float cdf, xpdf;
+                  gelu_terms(h8[e], cdf, xpdf);
+                  v[g * 8 + e] *= (cdf + xpdf);
+                }
               }
-          } else if (EPI == SWINB200_EPI_ADD_F32) {
-            float* d = reinterpret_cast<float*>(p.D) + (size_t)m * p.ldd + nb;
+          }
+        } else if (EPI == SWINB200_EPI_ADD_F32) {
+          if (row_ok) {
             const float* ax = reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + nb;
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < kChunkCols / 4; ++g)
               if (nb + g * 4 < p.N) {
                 const float4 a4 = *reinterpret_cast<const float4*>(ax + g * 4);
-                *reinterpret_cast<float4*>(d + g * 4) =
-                    make_float4(v[g * 4] + a4.x, v[g * 4 + 1] + a4.y, v[g * 4 + 2] + a4.z, v[g * 4 + 3] + a4.w);
+                v[g * 4 + 0] += a4.x; v[g * 4 + 1] += a4.y; v[g * 4 + 2] += a4.z; v[g * 4 + 3] += a4.w;
               }
-          } else {  // EPI_F32
-            float* d = reinterpret_cast<float*>(p.D) + (size_t)m * p.ldd + nb;
-            if (p.atomic_out) {
+          }
+        }
+        // ---- stage the chunk (and, for GELU, first the pre-activation) and hand it to the copy engine ----------
+        constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (nb + g * 4 < p.N)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + g * 4), "f"(v[g * 4]),
-                               "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
-                               : "memory");
-            } else {
+        for (int pass = 0; pass < kPasses; ++pass) {
+          if (issuer) bulk_wait_read0();            // the previous store has finished reading the staging buffer
+          group_bar(1 + grp);
+          if (kF32Out) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (nb + g * 4 < p.N)
-                  *reinterpret_cast<float4*>(d + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(staging_chunk(stg, r, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float t8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t8[e] = v[c * 8 + e];
+              if (EPI == SWINB200_EPI_BIAS_GELU && pass == 1) {
+                // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float h = Act<__nv_bfloat16>::round(t8[e]);
+                  float cdf, xpdf;
+                  gelu_terms(h, cdf, xpdf);
+                  t8[e] = h * cdf;
+                }
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(t8[0], t8[1]); pk.y = pack_bf16x2(t8[2], t8[3]);
+              pk.z = pack_bf16x2(t8[4], t8[5]); pk.w = pack_bf16x2(t8[6], t8[7]);
+              *reinterpret_cast<uint4*>(staging_chunk(stg, r, c)) = pk;
             }
+          }
+          fence_proxy_async_smem();
+          group_bar(1 + grp);
+          if (issuer) {
+            if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg, nb, m0);
+            else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg, nb, m0);
+            else tma_store_2d(&tmD, stg, nb, m0);
+            bulk_commit();
           }
         }
       }
@@ -254,6 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
+    if (issuer) bulk_wait0();   // all global writes of this CTA have completed before it exits
   }
 
   tc_fence_before();
@@ -279,21 +337,21 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle
-int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                      uint32_t box_outer) {
+// 2-D tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle
+int make_tmap_2d(CUtensorMap* m, bool f32, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                 uint32_t box_outer) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return SWINB200_ERR_CUDA;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
@@ -303,7 +361,8 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
+                     const GemmTcParams& p, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
@@ -313,7 +372,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmT
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = min(tiles, sm_count());
-  kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, tmD, tmD2, p);
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }
@@ -321,21 +380,21 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmT
 // Only the operand-major / epilogue pairs the model uses are instantiated:
 //   forward  (A k-major, B k-major) : BIAS, BIAS_GELU, F32
 //   dgrad    (A k-major, B n-major) : BIAS (no bias pointer), DGELU, ADD_F32, F32
-//   wgrad    (A m-major, B n-major) : F32 (plain or split-K atomic)
+//   wgrad    (A m-major, B n-major) : F32 (plain or split-K reduce-add)
 template <int BN>
-static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p,
-                    cudaStream_t s) {
+static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                    const CUtensorMap& tmD2, const GemmTcParams& p, cudaStream_t s) {
   if (!a_major && !b_major) {
-    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, false, SWINB200_EPI_BIAS>(tmA, tmB, p, s);
-    if (epi == SWINB200_EPI_BIAS_GELU) return launch_tc<BN, false, false, SWINB200_EPI_BIAS_GELU>(tmA, tmB, p, s);
-    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, false, SWINB200_EPI_F32>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, false, SWINB200_EPI_BIAS>(tmA, tmB, tmD, tmD2, p, s);
+    if (epi == SWINB200_EPI_BIAS_GELU) return launch_tc<BN, false, false, SWINB200_EPI_BIAS_GELU>(tmA, tmB, tmD, tmD2, p, s);
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, false, SWINB200_EPI_F32>(tmA, tmB, tmD, tmD2, p, s);
   } else if (!a_major && b_major) {
-    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, true, SWINB200_EPI_BIAS>(tmA, tmB, p, s);
-    if (epi == SWINB200_EPI_DGELU) return launch_tc<BN, false, true, SWINB200_EPI_DGELU>(tmA, tmB, p, s);
-    if (epi == SWINB200_EPI_ADD_F32) return launch_tc<BN, false, true, SWINB200_EPI_ADD_F32>(tmA, tmB, p, s);
-    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, true, SWINB200_EPI_F32>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_BIAS) return launch_tc<BN, false, true, SWINB200_EPI_BIAS>(tmA, tmB, tmD, tmD2, p, s);
+    if (epi == SWINB200_EPI_DGELU) return launch_tc<BN, false, true, SWINB200_EPI_DGELU>(tmA, tmB, tmD, tmD2, p, s);
+    if (epi == SWINB200_EPI_ADD_F32) return launch_tc<BN, false, true, SWINB200_EPI_ADD_F32>(tmA, tmB, tmD, tmD2, p, s);
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, false, true, SWINB200_EPI_F32>(tmA, tmB, tmD, tmD2, p, s);
   } else if (a_major && b_major) {
-    if (epi == SWINB200_EPI_F32) return launch_tc<BN, true, true, SWINB200_EPI_F32>(tmA, tmB, p, s);
+    if (epi == SWINB200_EPI_F32) return launch_tc<BN, true, true, SWINB200_EPI_F32>(tmA, tmB, tmD, tmD2, p, s);
   }
   set_error("gemm(tcgen05): combination a_major=%d b_major=%d epilogue=%d is not instantiated", a_major, b_major, epi);
   return SWINB200_ERR_UNSUPPORTED;
@@ -352,9 +411,10 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   SWB_CHECK_ARG(bias == nullptr || ((uintptr_t)bias % 16 == 0), "gemm(tcgen05): bias must be 16-byte aligned");
 
   const int BN = (N > 128) ? 256 : 128;
+  const bool f32_out = (epilogue == SWINB200_EPI_ADD_F32 || epilogue == SWINB200_EPI_F32);
   GemmTcParams p;
   p.M = M; p.N = N; p.K = K;
-  p.bias = bias; p.D = D; p.D2 = D2; p.aux = aux; p.ldd = ldd; p.ld_aux = ld_aux;
+  p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
   p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
   p.num_m_tiles = (M + GBM - 1) / GBM;
   p.num_n_tiles = (N + BN - 1) / BN;
@@ -363,17 +423,25 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD, tmD2;
   int e;
-  if (!a_major) e = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GBK, GBM);
-  else e = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GBK);
+  if (!a_major) e = make_tmap_2d(&tmA, false, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GBK, GBM);
+  else e = make_tmap_2d(&tmA, false, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GBK);
   if (e) return e;
-  if (!b_major) e = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)BN);
-  else e = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
+  if (!b_major) e = make_tmap_2d(&tmB, false, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)BN);
+  else e = make_tmap_2d(&tmB, false, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
   if (e) return e;
+  // output maps: one [128 rows x 128 bytes] box per staged chunk; the copy engine clips rows >= M and columns >= N
+  e = make_tmap_2d(&tmD, f32_out, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, f32_out ? 32 : 64, GBM);
+  if (e) return e;
+  tmD2 = tmD;
+  if (epilogue == SWINB200_EPI_BIAS_GELU) {
+    e = make_tmap_2d(&tmD2, false, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, GBM);
+    if (e) return e;
+  }
 
-  if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, p, stream);
-  return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, p, stream);
+  if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
+  return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
 }
 
 }  // namespace swinb200

@@ -58,6 +58,7 @@ class PatchEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode):
+        ctx.set_materialize_grads(False)   # no zero-filled gradient for the (non-differentiable) bf16 shadow output
         B, Cin, Hi, Wi = img.shape
         E = proj_w.shape[0]
         H, W = Hi // patch, Wi // patch
@@ -101,6 +102,7 @@ class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, xb, scale, bias, qkv_w, qkv_b, proj_w, proj_b, n1_w, n1_b, fc1_w, fc1_b, fc2_w, fc2_b, n2_w, n2_b,
                 dp1, dp2, geom, mode: ComputeMode):
+        ctx.set_materialize_grads(False)
         B, H, W, C = x.shape
         heads, Wh, Ww, s0, s1 = geom
         T = B * H * W
