@@ -142,6 +142,10 @@ int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, co
 int swinb200_debug_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mode, int b_mode,
                               int pad16, void* stream);
 
+/* bring-up aid: when buf != NULL the tcgen05 attention kernels write clock64() stamps per phase for CTAs < 4096
+ * into buf[cta*16 + phase] (int64).  Pass NULL to switch it off. */
+int swinb200_debug_attn_phase_buffer(void* buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,13 @@ using namespace ptx;
 
 constexpr int kMaxLP = 176;  // padded keys per window (multiple of 16); 9x18 = 162 -> 176
 
+// optional per-phase cycle stamps (bring-up aid): when non-null, CTA b writes clock64() deltas to g_phase[b*16 + i]
+__device__ long long* g_phase_buf = nullptr;
+#define SWB_STAMP(i)                                                                 \
+  do {                                                                               \
+    if (g_phase_buf != nullptr && threadIdx.x == 0 && blockIdx.x < 4096) g_phase_buf[blockIdx.x * 16 + (i)] = clock64(); \
+  } while (0)
+
 __host__ __device__ constexpr uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
@@ -46,6 +53,44 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float as_f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint4 pack8(const float (&v)[16], int o) {
+  uint4 r;
+  r.x = pack_bf16x2(v[o + 0], v[o + 1]); r.y = pack_bf16x2(v[o + 2], v[o + 3]);
+  r.z = pack_bf16x2(v[o + 4], v[o + 5]); r.w = pack_bf16x2(v[o + 6], v[o + 7]);
+  return r;
+}
+
+// Row tiles leave the kernel through shared memory: each thread parks its [1 x D] bf16 row (pitch kRowPitch keeps the
+// 16-byte stores conflict-free), then the CTA writes token rows with consecutive threads on consecutive 16-byte pieces,
+// so every global store instruction covers whole 192-byte rows instead of 32 scattered 16-byte fragments.
+constexpr int kRowPitch = 208;
+template <int D>
+__device__ __forceinline__ void park_row(unsigned char* stage, int row, const float (&v)[D]) {
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) {
+    uint4 pk;
+    pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+    pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(stage + row * kRowPitch + c * 16) = pk;
+  }
+}
+// rows [0, nrows) of `stage` -> dst[tok[slot0 + row] * ld + col0 ...]; executed by `nthr` threads with index `t`
+template <int D>
+__device__ __forceinline__ void scatter_rows(const unsigned char* stage, int nrows, const int* tok, int slot0,
+                                             __nv_bfloat16* dst, int ld, int col0, int t, int nthr) {
+  constexpr int kPieces = D / 8;
+  for (int i = t; i < nrows * kPieces; i += nthr) {
+    const int row = i / kPieces, c = i - row * kPieces;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + row * kRowPitch + c * 16);
+    *reinterpret_cast<uint4*>(dst + (size_t)tok[slot0 + row] * ld + col0 + c * 8) = v;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // forward
@@ -61,6 +106,7 @@ struct FwdSmem {
   static constexpr int kOffTok = kOffP + 2 * kPTile;
   static constexpr int kOffBar = kOffTok + kMaxLP * 4;
   static constexpr int kBytes = kOffBar + 64;
+  static_assert(256 * kRowPitch <= 2 * kPTile, "output staging must fit in the P tiles");
 };
 
 template <int D>
@@ -68,6 +114,7 @@ __global__ void __launch_bounds__(256, 1)
 attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ scale_p, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const AttnGeom g) {
   using SM = FwdSmem<D>;
+  constexpr float kLog2e = 1.4426950408889634f;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sQ = smem + SM::kOffQ;
   unsigned char* sK = smem + SM::kOffK;
@@ -78,6 +125,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SWB_STAMP(0);
   const int head = blockIdx.x % g.heads;
   const int w = (blockIdx.x / g.heads) % g.nW;
   const int b = blockIdx.x / (g.heads * g.nW);
@@ -97,6 +145,8 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
       label_split = 0;
     }
   }
+  // "plain" windows: no position bias and a single region label -> logits are just scale * cos
+  const bool plain = (bias == nullptr) && !(label_split > 0 && label_split < L);
   for (int n = tid; n < LP; n += 256) {
     int rr;
     tok[n] = (n < L) ? win_token(g, b, w, n, rr) : -1;
@@ -115,6 +165,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
     *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
+  SWB_STAMP(1);
 
   // ---- gather Q^, K^, V of this (window, head): one 16-byte cp.async per (token, 8 channels) ----------------------
   {
@@ -132,6 +183,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
+  SWB_STAMP(2);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -152,52 +204,106 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
   const int n = t * 128 + r;                     // slot (query) index inside the window
   const bool row_ok = (t < ntiles) && (n < L);
-  const float scale_l2 = scale_p[head] * 1.4426950408889634f;   // work in the log2 domain
-  const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
-  const int my_label = (n >= label_split) ? 1 : 0;
+  const float scale_l2 = scale_p[head] * kLog2e;  // work in the log2 domain
   const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * kMaxLP);
   float row_sum = 0.f, row_max = -INFINITY;
 
   mbar_wait(&bars[0], 0, 500);
+  SWB_STAMP(3);
   tc_fence_after();
   if (t < ntiles) {
-    // pass 1: row maximum of the (log2-domain) logits
-    for (int c0 = 0; c0 < LP; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_32x16(t_s + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int key = c0 + j;
-        float s = __uint_as_float(v[j]) * scale_l2;
-        if (brow != nullptr && key < L) s += brow[key] * 1.4426950408889634f;
-        if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * 1.4426950408889634f;
-        if (key < L) row_max = fmaxf(row_max, s);
-      }
-    }
-    // pass 2: p = 2^(s - max), row sum, bf16 P tile
     unsigned char* myP = sP + t * SM::kPTile + r * 16;
-    for (int c0 = 0; c0 < LP; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_32x16(t_s + c0, v);
-      tmem_ld_wait();
-      float p[16];
+    if (plain) {
+      // pass 1: max of the raw cosines (scale > 0); TMEM loads run one chunk ahead of the arithmetic.
+      // Pad keys hold exact zeros (zeroed K^ rows): including them can only raise the max, which is harmless.
+      uint32_t va[16], vb[16];
+      float mx = -INFINITY;
+      tmem_ld_32x16(t_s, va);
+      for (int c0 = 0; c0 < LP; c0 += 32) {
+        tmem_ld_wait();
+        const bool has_b = c0 + 16 < LP;
+        if (has_b) tmem_ld_32x16(t_s + c0 + 16, vb);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int key = c0 + j;
-        float s = __uint_as_float(v[j]) * scale_l2;
-        if (brow != nullptr && key < L) s += brow[key] * 1.4426950408889634f;
-        if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * 1.4426950408889634f;
-        const float e = (key < L && row_ok) ? exp2f(s - row_max) : 0.f;
-        // the probabilities that multiply V are the bf16-rounded ones; normalise by their sum
-        p[j] = __bfloat162float(__float2bfloat16_rn(e));
-        row_sum += p[j];
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, as_f(va[j]));
+        if (has_b) {
+          tmem_ld_wait();
+          if (c0 + 32 < LP) tmem_ld_32x16(t_s + c0 + 32, va);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, as_f(vb[j]));
+        }
       }
-      uint4 lo, hi;
-      lo.x = pack_bf16x2(p[0], p[1]);  lo.y = pack_bf16x2(p[2], p[3]);  lo.z = pack_bf16x2(p[4], p[5]);  lo.w = pack_bf16x2(p[6], p[7]);
-      hi.x = pack_bf16x2(p[8], p[9]);  hi.y = pack_bf16x2(p[10], p[11]); hi.z = pack_bf16x2(p[12], p[13]); hi.w = pack_bf16x2(p[14], p[15]);
-      *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = lo;
-      *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = hi;
+      row_max = mx * scale_l2;
+      const float neg_m = -row_max;
+      // pass 2: p = 2^(scale*cos - max) -> bf16 P tile; fp32 row sum
+      tmem_ld_32x16(t_s, va);
+      for (int c0 = 0; c0 < LP; c0 += 32) {
+        tmem_ld_wait();
+        const bool has_b = c0 + 16 < LP;
+        if (has_b) tmem_ld_32x16(t_s + c0 + 16, vb);
+        {
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(as_f(va[j]), scale_l2, neg_m));
+          if (c0 + 16 > L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c0 + j >= L) p[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) row_sum += p[j];
+          *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = pack8(p, 0);
+          *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = pack8(p, 8);
+        }
+        if (has_b) {
+          tmem_ld_wait();
+          if (c0 + 32 < LP) tmem_ld_32x16(t_s + c0 + 32, va);
+          const int c1 = c0 + 16;
+          float p[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(as_f(vb[j]), scale_l2, neg_m));
+          if (c1 + 16 > L) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c1 + j >= L) p[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) row_sum += p[j];
+          *reinterpret_cast<uint4*>(myP + (c1 / 8) * SM::kPCS) = pack8(p, 0);
+          *reinterpret_cast<uint4*>(myP + (c1 / 8 + 1) * SM::kPCS) = pack8(p, 8);
+        }
+      }
+    } else {
+      // general path: continuous position bias and / or the shifted-window mask (-100 across region labels)
+      const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+      const int my_label = (n >= label_split) ? 1 : 0;
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_s + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int key = c0 + j;
+          float s = as_f(v[j]) * scale_l2;
+          if (brow != nullptr && key < L) s += brow[key] * kLog2e;
+          if (((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
+          if (key < L) row_max = fmaxf(row_max, s);
+        }
+      }
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_s + c0, v);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int key = c0 + j;
+          float s = as_f(v[j]) * scale_l2;
+          if (brow != nullptr && key < L) s += brow[key] * kLog2e;
+          if (((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
+          p[j] = (key < L && row_ok) ? ex2_approx(s - row_max) : 0.f;
+          row_sum += p[j];
+        }
+        *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = pack8(p, 0);
+        *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = pack8(p, 8);
+      }
     }
     if (row_ok)
       lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] = (row_max + log2f(row_sum)) * 0.6931471805599453f;
@@ -205,6 +311,7 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
   tc_fence_before();
   __syncthreads();            // every thread has finished reading S: O may overwrite its columns
+  SWB_STAMP(4);
 
   // ---- O_t = P_t V  (accumulator aliases S_t) ----------------------------------------------------------------------------
   if (tid == 0) {
@@ -218,33 +325,35 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
     umma_commit(&bars[1]);
   }
   mbar_wait(&bars[1], 0, 501);
+  SWB_STAMP(5);
   tc_fence_after();
+  // the P tiles are dead once the MMAs have completed: reuse them to stage the output rows
   if (t < ntiles) {
-    const float inv = row_ok ? 1.0f / row_sum : 0.f;
-    __nv_bfloat16* orow = row_ok ? o + (size_t)tok[n] * g.C + head * D : nullptr;
+    const float inv = 1.0f / row_sum;
+    float ov[D];
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_32x16(t_s + c0, v);
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_s + c0, v);
       tmem_ld_wait();
-      if (row_ok) {
-        float a8[8], b8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a8[j] = __uint_as_float(v[j]) * inv;
-          b8[j] = __uint_as_float(v[8 + j]) * inv;
-        }
-        st8(orow + c0, a8);
-        st8(orow + c0 + 8, b8);
-      }
+      for (int j = 0; j < 32; ++j) ov[c0 + j] = as_f(v[j]) * inv;
     }
+    if (row_ok) park_row<D>(sP, n, ov);
   }
   tc_fence_before();
   __syncthreads();
+  scatter_rows<D>(sP, L, tok, 0, o, g.C, head * D, tid, 256);
+  SWB_STAMP(6);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+int attn_set_phase_buffer(long long* buf) {
+  SWB_CUDA(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
+  return SWINB200_OK;
 }
 
 static int make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
@@ -328,6 +437,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SWB_STAMP(0);
   const int head = blockIdx.x % g.heads;
   const int w = (blockIdx.x / g.heads) % g.nW;
   const int b = blockIdx.x / (g.heads * g.nW);
@@ -363,6 +473,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
     *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
+  SWB_STAMP(1);
   {
     const int per_op = L * SM::kChunks;
     for (int i = tid; i < 4 * per_op; i += 256) {
@@ -395,6 +506,7 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
+  SWB_STAMP(2);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), g0 = smem_u32(sG), p0 = smem_u32(sP), ds0 = smem_u32(sDS);
@@ -403,10 +515,12 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   const float scale = scale_p[head];
   const float scale_l2 = scale * kLog2e;
   uint32_t parity = 0;
+  const bool plain = (bias == nullptr) && !(label_split > 0 && label_split < L);
 
   const int r = (warp & 3) * 32 + lane;                 // row inside the current 128-row tile == TMEM lane
-  const int half = warp >> 2;                           // which half of the LP columns this thread handles
-  const int c_begin = half * (LP / 2), c_end = c_begin + LP / 2;    // LP/2 is a multiple of 8
+  const int half = warp >> 2;                           // which part of the LP columns this thread handles
+  const int c_split = ((LP + 31) / 32) * 16;            // both parts are multiples of 16 columns (176 -> 96 + 80)
+  const int c_begin = half ? c_split : 0, c_end = half ? LP : c_split;
   const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   float dsc_acc = 0.f;
 
@@ -425,43 +539,94 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 600 + t);
+    SWB_STAMP(3);
     parity ^= 1;
     tc_fence_after();
     {
       const int n = t * 128 + r;                        // query slot of this thread
       const bool row_ok = n < L;
-      const float my_lse = lse2[min(n, LP - 1)];
-      const float my_D = Dv[min(n, LP - 1)];
-      const int my_label = (n >= label_split) ? 1 : 0;
-      const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
-      float* dbrow = (dbias != nullptr && row_ok) ? dbias + ((size_t)head * L + n) * L : nullptr;
-      for (int c0 = c_begin; c0 < c_end; c0 += 8) {
-        uint32_t sv[8], pv[8];
-        tmem_ld_32x8(t_lane + c0, sv);
-        tmem_ld_32x8(t_lane + kMaxLP + c0, pv);
-        tmem_ld_wait();
-        float ds[8];
+      const float my_lse = row_ok ? lse2[n] : INFINITY;  // pad rows: p = 2^(-inf) = 0
+      const float my_D = row_ok ? Dv[n] : 0.f;
+      unsigned char* myDS = sDS + r * 16;
+      float dsc_tile = 0.f;
+      if (plain) {
+        // dS = P o (dP - D), P = 2^(scale*cos - lse); loads of the next 16 columns overlap this chunk's arithmetic
+        uint32_t sa[16], pa[16], sb[16], pb[16];
+        tmem_ld_32x16(t_lane + c_begin, sa);
+        tmem_ld_32x16(t_lane + kMaxLP + c_begin, pa);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 16 < c_end;
+          if (has_b) {
+            tmem_ld_32x16(t_lane + c0 + 16, sb);
+            tmem_ld_32x16(t_lane + kMaxLP + c0 + 16, pb);
+          }
+          {
+            float ds[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int key = c0 + j;
-          const float cosv = __uint_as_float(sv[j]);
-          float s = cosv * scale_l2;
-          if (brow != nullptr && key < L) s += brow[key] * kLog2e;
-          if (shifted && ((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
-          const float p = (key < L && row_ok) ? exp2f(s - my_lse) : 0.f;
-          // pad rows / pad keys read whatever follows the real rows in shared memory: keep them exactly zero
-          ds[j] = (key < L && row_ok) ? p * (__uint_as_float(pv[j]) - my_D) : 0.f;
-          if (key < L && row_ok) dsc_acc = fmaf(ds[j], cosv, dsc_acc);
-          if (dbrow != nullptr && key < L) atomicAdd(dbrow + key, ds[j]);
+            for (int j = 0; j < 16; ++j) {
+              const float cosv = as_f(sa[j]);
+              const float p = ex2_approx(fmaf(cosv, scale_l2, -my_lse));
+              ds[j] = p * (as_f(pa[j]) - my_D);
+              if (c0 + 16 > L && c0 + j >= L) ds[j] = 0.f;
+              dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            }
+            *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+            *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+          }
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < c_end) {
+              tmem_ld_32x16(t_lane + c0 + 32, sa);
+              tmem_ld_32x16(t_lane + kMaxLP + c0 + 32, pa);
+            }
+            const int c1 = c0 + 16;
+            float ds[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float cosv = as_f(sb[j]);
+              const float p = ex2_approx(fmaf(cosv, scale_l2, -my_lse));
+              ds[j] = p * (as_f(pb[j]) - my_D);
+              if (c1 + 16 > L && c1 + j >= L) ds[j] = 0.f;
+              dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            }
+            *reinterpret_cast<uint4*>(myDS + (c1 / 8) * SM::kPCS) = pack8(ds, 0);
+            *reinterpret_cast<uint4*>(myDS + (c1 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+          }
         }
-        uint4 pk;
-        pk.x = pack_bf16x2(ds[0], ds[1]); pk.y = pack_bf16x2(ds[2], ds[3]); pk.z = pack_bf16x2(ds[4], ds[5]); pk.w = pack_bf16x2(ds[6], ds[7]);
-        *reinterpret_cast<uint4*>(sDS + (c0 / 8) * SM::kPCS + r * 16) = pk;
+      } else {
+        const int my_label = (n >= label_split) ? 1 : 0;
+        const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+        float* dbrow = (dbias != nullptr && row_ok) ? dbias + ((size_t)head * L + n) * L : nullptr;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+          uint32_t sv[16], pv[16];
+          tmem_ld_32x16(t_lane + c0, sv);
+          tmem_ld_32x16(t_lane + kMaxLP + c0, pv);
+          tmem_ld_wait();
+          float ds[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int key = c0 + j;
+            const float cosv = as_f(sv[j]);
+            float s = cosv * scale_l2;
+            if (brow != nullptr && key < L) s += brow[key] * kLog2e;
+            if (((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
+            const float p = (key < L && row_ok) ? ex2_approx(s - my_lse) : 0.f;
+            // pad rows / pad keys read whatever follows the real rows in shared memory: keep them exactly zero
+            ds[j] = (key < L && row_ok) ? p * (as_f(pv[j]) - my_D) : 0.f;
+            if (key < L && row_ok) dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            if (dbrow != nullptr && key < L) atomicAdd(dbrow + key, ds[j]);
+          }
+          *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+          *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+        }
       }
+      if (row_ok) dsc_acc += dsc_tile;   // pad rows carry garbage cosines (their P is 0, but 0 * NaN would poison the sum)
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    SWB_STAMP(4);
     if (tid == 0) {
       tc_fence_after();
       for (int k = 0; k < LP / 16; ++k)     // dQ^_t = dS K^   (K^ read n-major: rows = keys = k-dimension)
@@ -470,21 +635,23 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 610 + t);
+    SWB_STAMP(5);
     parity ^= 1;
     tc_fence_after();
+    const int rows_here = min(128, L - t * 128);
     if (half == 0) {
-      // dq = inv_norm * (dq^ - q^ <q^, dq^>),  dq^ = scale * (dS K^)
+      // dq = inv_norm * (dq^ - q^ <q^, dq^>),  dq^ = scale * (dS K^);  the dS tile is dead: stage the rows there
       const int n = t * 128 + r;
       const bool row_ok = n < L;
       float dq[D];
       float dot = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_lane + c0, v);
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dq[c0 + j] = __uint_as_float(v[j]) * scale;
+        for (int j = 0; j < 32; ++j) dq[c0 + j] = as_f(v[j]) * scale;
       }
       if (row_ok) {
         float qh[D];
@@ -499,18 +666,16 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
           }
         }
         const float inq = inv_norm[(size_t)tok[n] * 2 * g.heads + head];
-        __nv_bfloat16* dst = dqkv + (size_t)tok[n] * C3 + head * D;
 #pragma unroll
-        for (int c = 0; c < D; c += 8) {
-          float o8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = inq * (dq[c + e] - qh[c + e] * dot);
-          st8(dst + c, o8);
-        }
+        for (int c = 0; c < D; ++c) dq[c] = inq * (dq[c] - qh[c] * dot);
+        park_row<D>(sDS, r, dq);
       }
     }
     tc_fence_before();
-    __syncthreads();      // dQ^ has been read: the next tile's S may overwrite it
+    __syncthreads();      // dQ^ has been read (the next S may overwrite it) and the staged rows are complete
+    scatter_rows<D>(sDS, rows_here, tok, t * 128, dqkv, C3, head * D, tid, 256);
+    __syncthreads();      // staging drained before the next tile's dS lands in the same buffer
+    SWB_STAMP(6);
   }
 
   // ================================ sweep B: key-major -> dk, dv ================================
@@ -528,38 +693,58 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 620 + u);
+    SWB_STAMP(7);
     parity ^= 1;
     tc_fence_after();
     {
       const int jk = u * 128 + r;                       // key slot of this thread
       const bool key_ok = jk < L;
       const int key_label = (jk >= label_split) ? 1 : 0;
-      for (int c0 = c_begin; c0 < c_end; c0 += 8) {     // columns = queries
-        uint32_t sv[8], pv[8];
-        tmem_ld_32x8(t_lane + c0, sv);
-        tmem_ld_32x8(t_lane + kMaxLP + c0, pv);
-        tmem_ld_wait();
-        float pp[8], ds[8];
+      unsigned char* myP = sP + r * 16;
+      unsigned char* myDS = sDS + r * 16;
+      // columns = queries; lse2[q] = +inf for pad queries -> P = 0 there.  Pad key rows only feed discarded output rows,
+      // but they are zeroed so that no NaN ever enters the tensor pipe.
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t sv[16], pv[16];
+        tmem_ld_32x16(t_lane + c0, sv);
+        tmem_ld_32x16(t_lane + kMaxLP + c0, pv);
+        float ls[16], dd[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int qi = c0 + j;
-          float s = __uint_as_float(sv[j]) * scale_l2;
-          if (bias != nullptr && key_ok && qi < L) s += bias[((size_t)head * L + qi) * L + jk] * kLog2e;
-          if (shifted && ((qi >= label_split) ? 1 : 0) != key_label) s += -100.0f * kLog2e;
-          const float p = key_ok ? exp2f(s - lse2[qi]) : 0.f;      // lse2 = +inf for pad queries -> p = 0
-          pp[j] = p;
-          ds[j] = (key_ok && qi < L) ? p * (__uint_as_float(pv[j]) - Dv[qi]) : 0.f;
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(&ls[j]) = *reinterpret_cast<const float4*>(&lse2[c0 + j]);
+          *reinterpret_cast<float4*>(&dd[j]) = *reinterpret_cast<const float4*>(&Dv[c0 + j]);
         }
-        uint4 pk, dk;
-        pk.x = pack_bf16x2(pp[0], pp[1]); pk.y = pack_bf16x2(pp[2], pp[3]); pk.z = pack_bf16x2(pp[4], pp[5]); pk.w = pack_bf16x2(pp[6], pp[7]);
-        dk.x = pack_bf16x2(ds[0], ds[1]); dk.y = pack_bf16x2(ds[2], ds[3]); dk.z = pack_bf16x2(ds[4], ds[5]); dk.w = pack_bf16x2(ds[6], ds[7]);
-        *reinterpret_cast<uint4*>(sP + (c0 / 8) * SM::kPCS + r * 16) = pk;
-        *reinterpret_cast<uint4*>(sDS + (c0 / 8) * SM::kPCS + r * 16) = dk;
+        tmem_ld_wait();
+        float pp[16], ds[16];
+        if (plain) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p = ex2_approx(fmaf(as_f(sv[j]), scale_l2, -ls[j]));
+            pp[j] = key_ok ? p : 0.f;
+            ds[j] = key_ok ? p * (as_f(pv[j]) - dd[j]) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int qi = c0 + j;
+            float s = as_f(sv[j]) * scale_l2;
+            if (bias != nullptr && key_ok && qi < L) s += bias[((size_t)head * L + qi) * L + jk] * kLog2e;
+            if (((qi >= label_split) ? 1 : 0) != key_label) s += -100.0f * kLog2e;
+            const float p = key_ok ? ex2_approx(s - ls[j]) : 0.f;
+            pp[j] = p;
+            ds[j] = (key_ok && qi < L) ? p * (as_f(pv[j]) - dd[j]) : 0.f;
+          }
+        }
+        *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = pack8(pp, 0);
+        *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = pack8(pp, 8);
+        *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+        *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
       }
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    SWB_STAMP(8);
     if (tid == 0) {
       tc_fence_after();
       for (int k = 0; k < LP / 16; ++k)     // dV_u = P^T dO   (dO read n-major: rows = queries = k-dimension)
@@ -571,33 +756,29 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 630 + u);
+    SWB_STAMP(9);
     parity ^= 1;
     tc_fence_after();
+    const int rows_here = min(128, L - u * 128);
     {
+      // warps 0-3: dv rows (staged in the P tile); warps 4-7: dk rows (staged in the dS tile)
       const int jk = u * 128 + r;
       const bool key_ok = jk < L;
       float acc[D];
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_lane + half * kMaxLP + c0, v);
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + half * kMaxLP + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = as_f(v[j]);
       }
       if (key_ok) {
-        if (half == 0) {                                 // dv
-          __nv_bfloat16* dst = dqkv + (size_t)tok[jk] * C3 + 2 * C + head * D;
-#pragma unroll
-          for (int c = 0; c < D; c += 8) {
-            float o8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = acc[c + e];
-            st8(dst + c, o8);
-          }
-        } else {                                         // dk = inv_norm * (dk^ - k^ <k^, dk^>)
-          float kh[D];
+        if (half == 0) {
+          park_row<D>(sP, r, acc);
+        } else {                                         // dk = inv_norm * (dk^ - k^ <k^, dk^>), dk^ = scale * (dS^T Q^)
           float dot = 0.f;
+          float kh[D];
 #pragma unroll
           for (int c = 0; c < D / 8; ++c) {
             float t8[8];
@@ -610,19 +791,19 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
             }
           }
           const float ink = inv_norm[(size_t)tok[jk] * 2 * g.heads + g.heads + head];
-          __nv_bfloat16* dst = dqkv + (size_t)tok[jk] * C3 + C + head * D;
 #pragma unroll
-          for (int c = 0; c < D; c += 8) {
-            float o8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = ink * (acc[c + e] - kh[c + e] * dot);
-            st8(dst + c, o8);
-          }
+          for (int c = 0; c < D; ++c) acc[c] = ink * (acc[c] - kh[c] * dot);
+          park_row<D>(sDS, r, acc);
         }
       }
     }
     tc_fence_before();
     __syncthreads();
+    // 128 threads drain each staging tile with whole-row stores
+    if (half == 0) scatter_rows<D>(sP, rows_here, tok, u * 128, dqkv, C3, 2 * C + head * D, tid, 128);
+    else scatter_rows<D>(sDS, rows_here, tok, u * 128, dqkv, C3, C + head * D, tid - 128, 128);
+    __syncthreads();
+    SWB_STAMP(10);
   }
 
   // ---- d(scale) = sum dS o cos -----------------------------------------------------------------------------------------
@@ -660,3 +841,5 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
 }
 
 }  // namespace swinb200
+
+extern "C" int swinb200_debug_attn_phase_buffer(void* buf) { return swinb200::attn_set_phase_buffer((long long*)buf); }

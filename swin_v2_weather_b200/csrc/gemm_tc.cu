@@ -3,9 +3,9 @@
 // Persistent, warp-specialised, one CTA per SM (320 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
-//   warps 2..9  epilogue       (two groups of 4 warps; each group owns every other 128-byte column chunk of the tile:
-//                               tcgen05.ld -> fused epilogue in registers -> swizzled smem staging -> TMA store /
-//                               TMA reduce-add, so global writes are full 128-byte rows issued by the copy engine)
+//   warps 2..9  epilogue       (two groups of 4 warps; each group owns every other 64-byte column chunk of the tile:
+//                               tcgen05.ld -> fused epilogue in registers -> swizzled, double-buffered smem staging -> TMA store /
+//                               TMA reduce-add, so global writes are whole 64-byte row pieces issued by the copy engine)
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
 // token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
@@ -20,7 +20,7 @@ using namespace ptx;
 constexpr int GBM = 128;  // UMMA M (cta_group::1)
 constexpr int GBK = 64;   // k per pipeline stage (one 128-byte swizzle row of bf16)
 constexpr int kGemmThreads = 320;
-constexpr int kStagingBytes = 128 * 128;   // one [128 rows x 128 B] output chunk per epilogue group
+constexpr int kStagingBytes = 128 * 64;    // one [128 rows x 64 B] output chunk; two per epilogue group (double-buffered)
 
 struct GemmTcParams {
   int M, N, K;
@@ -39,23 +39,38 @@ struct GemmCfg {
   static constexpr int kStages = (BN >= 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOffStaging = kStages * kStage;
-  static constexpr int kOffBars = kOffStaging + 2 * kStagingBytes;
+  static constexpr int kOffBars = kOffStaging + 4 * kStagingBytes;
   static constexpr int kSmem = kOffBars + 256 + 1024 /* alignment slack */;
 };
 
-// exact-GELU pieces from one exponential: Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 on erf), fast enough to keep the
-// epilogue under the MMA time of a K=768 tile.  Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  phi(x) = exp(-x^2/2) / sqrt(2 pi).
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& x_pdf) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-z * z);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
-  x_pdf = x * 0.39894228040143267794f * e;
+// GELU in the epilogue has an instruction budget: a 128x256 tile with K = 768 keeps the tensor pipe busy for ~6.1k
+// cycles, in which 8 epilogue warps must process 32k elements -> <= ~19 issue slots per element.  erff()/expf() cost
+// ~30, so the normal CDF is evaluated as  Phi(x) = 0.5 + xc * P(xc^2),  xc = clamp(x, -4, 4),  with a degree-7 minimax
+// polynomial in x^2 (|Phi error| <= 7.5e-5 on the clamp range, 3.2e-5 beyond it; the exact-erf CUDA-core kernels remain
+// the reference used by the fp32 validation mode).
+__device__ __forceinline__ float normal_cdf_fast(float x) {
+  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float u = xc * xc;
+  float p = -1.5809101805430714e-09f;
+  p = fmaf(p, u, 1.21718073842203e-07f);
+  p = fmaf(p, u, -4.101022113900399e-06f);
+  p = fmaf(p, u, 8.066916052484885e-05f);
+  p = fmaf(p, u, -0.001048215082846582f);
+  p = fmaf(p, u, 0.009664907120168209f);
+  p = fmaf(p, u, -0.0661754235625267f);
+  p = fmaf(p, u, 0.3988475203514099f);
+  return fmaf(xc, p, 0.5f);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return x * normal_cdf_fast(x); }
+// d/dx [x Phi(x)] = Phi(x) + x phi(x),  phi(x) = exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
+  return fmaf(x * 0.39894228040143267794f, e, normal_cdf_fast(x));
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -72,12 +87,14 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-// 16-byte chunk `c` (0..7) of staging row `r`, 128B-swizzled exactly as the TMA store expects
+// 16-byte chunk `c` (0..3) of the 64-byte staging row `r`, 64B-swizzled exactly as the TMA store expects
+// (address bits [4,6) ^= bits [7,9)); eight consecutive rows land in eight distinct 16-byte bank groups.
 __device__ __forceinline__ unsigned char* staging_chunk(unsigned char* buf, int r, int c) {
-  return buf + r * 128 + ((c ^ (r & 7)) << 4);
+  return buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -86,8 +103,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmTcParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr bool kF32Out = (EPI == SWINB200_EPI_ADD_F32 || EPI == SWINB200_EPI_F32);
-  constexpr int kChunkCols = kF32Out ? 32 : 64;          // 128 bytes of output per row per chunk
+  constexpr int kChunkCols = kF32Out ? 16 : 32;          // 64 bytes of output per row per chunk
   constexpr int kNumChunks = BN / kChunkCols;
+  constexpr bool kHasAux = (EPI == SWINB200_EPI_DGELU || EPI == SWINB200_EPI_ADD_F32);
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
@@ -203,8 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;     // row inside the tile
     const bool issuer = (ew & 3) == 0 && lane == 0;
-    unsigned char* stg = smem + Cfg::kOffStaging + grp * kStagingBytes;
+    unsigned char* stg0 = smem + Cfg::kOffStaging + grp * 2 * kStagingBytes;   // two staging buffers per group
     int local = 0;
+    uint32_t nstore = 0;                   // chunks staged so far by this group (selects the staging buffer)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int rest = tile / p.split_k;
       const int n0 = (rest % p.num_n_tiles) * BN;
@@ -216,18 +235,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m = m0 + r;
       const bool row_ok = m < p.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+      // epilogue operand (h for DGELU, the fp32 residual gradient for ADD_F32): 64 bytes per row per chunk, fetched one
+      // chunk ahead into registers so its latency hides behind the previous chunk's arithmetic
+      uint4 aux_nxt[4];
+      auto aux_fetch = [&](int chn) {
+        if (kHasAux) {
+          const int nbn = n0 + chn * kChunkCols;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.aux) +
+                                     ((size_t)m * p.ld_aux + nbn) * (kF32Out ? 4 : 2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            aux_nxt[q] = (row_ok && chn < kNumChunks && nbn + q * (kChunkCols / 4) < p.N)
+                             ? __ldg(reinterpret_cast<const uint4*>(src) + q) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      aux_fetch(grp);
 #pragma unroll 1
       for (int ch = grp; ch < kNumChunks; ch += 2) {
         const int nb = n0 + ch * kChunkCols;
         if (nb >= p.N) break;                       // whole chunk beyond N (uniform across the group)
-        float v[kChunkCols];
+        uint4 aux_cur[4];
+        if (kHasAux) {
 #pragma unroll
-        for (int q = 0; q < kChunkCols / 32; ++q) {
+          for (int q = 0; q < 4; ++q) aux_cur[q] = aux_nxt[q];
+          aux_fetch(ch + 2);
+        }
+        float v[kChunkCols];
+        if (kChunkCols == 32) {
           uint32_t rr[32];
-          tmem_ld_32x32(t_row + ch * kChunkCols + q * 32, rr);
+          tmem_ld_32x32(t_row + ch * kChunkCols, rr);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[q * 32 + i] = __uint_as_float(rr[i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        } else {
+          uint32_t rr[16];
+          tmem_ld_32x16(t_row + ch * kChunkCols, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
         }
         if (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU) {
           if (p.bias != nullptr) {
@@ -239,61 +284,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
           }
         } else if (EPI == SWINB200_EPI_DGELU) {
-          if (row_ok) {
-            const __nv_bfloat16* hx = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + nb;
 #pragma unroll
-            for (int g = 0; g < kChunkCols / 8; ++g)
-              if (nb + g * 8 < p.N) {
-                float h8[8];
-                ld8(hx + g * 8, h8);
+          for (int g = 0; g < 4; ++g) {           // 4 x (8 bf16 of h)
+            float h8[8];
+            unpack_bf16x2(aux_cur[g].x, h8[0], h8[1]); unpack_bf16x2(aux_cur[g].y, h8[2], h8[3]);
+            unpack_bf16x2(aux_cur[g].z, h8[4], h8[5]); unpack_bf16x2(aux_cur[g].w, h8[6], h8[7]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float cdf, xpdf;
-                  gelu_terms(h8[e], cdf, xpdf);
-                  v[g * 8 + e] *= (cdf + xpdf);
-                }
-              }
+            for (int e = 0; e < 8; ++e) v[g * 8 + e] *= gelu_grad_fast(h8[e]);
           }
         } else if (EPI == SWINB200_EPI_ADD_F32) {
-          if (row_ok) {
-            const float* ax = reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + nb;
 #pragma unroll
-            for (int g = 0; g < kChunkCols / 4; ++g)
-              if (nb + g * 4 < p.N) {
-                const float4 a4 = *reinterpret_cast<const float4*>(ax + g * 4);
-                v[g * 4 + 0] += a4.x; v[g * 4 + 1] += a4.y; v[g * 4 + 2] += a4.z; v[g * 4 + 3] += a4.w;
-              }
+          for (int g = 0; g < 4; ++g) {           // 4 x (4 fp32)
+            v[g * 4 + 0] += __uint_as_float(aux_cur[g].x); v[g * 4 + 1] += __uint_as_float(aux_cur[g].y);
+            v[g * 4 + 2] += __uint_as_float(aux_cur[g].z); v[g * 4 + 3] += __uint_as_float(aux_cur[g].w);
           }
         }
-        // ---- stage the chunk (and, for GELU, first the pre-activation) and hand it to the copy engine ----------
-        constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
+        // ---- stage the chunk and hand it to the copy engine.  Staging is double-buffered: the store issued two chunks
+        //      ago must have finished *reading* its buffer; GELU stages the pre-activation and the activation at once.
+        if (EPI == SWINB200_EPI_BIAS_GELU) {
+          if (issuer) bulk_wait_read0();
+          group_bar(1 + grp);
 #pragma unroll
-        for (int pass = 0; pass < kPasses; ++pass) {
-          if (issuer) bulk_wait_read0();            // the previous store has finished reading the staging buffer
+          for (int c = 0; c < 4; ++c) {
+            // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h
+            uint4 ph, pg;
+            ph.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); ph.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+            ph.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); ph.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+            float h8[8];
+            unpack_bf16x2(ph.x, h8[0], h8[1]); unpack_bf16x2(ph.y, h8[2], h8[3]);
+            unpack_bf16x2(ph.z, h8[4], h8[5]); unpack_bf16x2(ph.w, h8[6], h8[7]);
+            float g8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g8[e] = gelu_fast(h8[e]);
+            pg.x = pack_bf16x2(g8[0], g8[1]); pg.y = pack_bf16x2(g8[2], g8[3]); pg.z = pack_bf16x2(g8[4], g8[5]); pg.w = pack_bf16x2(g8[6], g8[7]);
+            *reinterpret_cast<uint4*>(staging_chunk(stg0, r, c)) = ph;
+            *reinterpret_cast<uint4*>(staging_chunk(stg0 + kStagingBytes, r, c)) = pg;
+          }
+          fence_proxy_async_smem();
+          group_bar(1 + grp);
+          if (issuer) {
+            tma_store_2d(&tmD2, stg0, nb, m0);
+            tma_store_2d(&tmD, stg0 + kStagingBytes, nb, m0);
+            bulk_commit();
+          }
+        } else {
+          unsigned char* stg = stg0 + (nstore & 1) * kStagingBytes;
+          ++nstore;
+          if (issuer) bulk_wait_read1();
           group_bar(1 + grp);
           if (kF32Out) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < 4; ++c)
               *reinterpret_cast<float4*>(staging_chunk(stg, r, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
           } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float t8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) t8[e] = v[c * 8 + e];
-              if (EPI == SWINB200_EPI_BIAS_GELU && pass == 1) {
-                // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float h = Act<__nv_bfloat16>::round(t8[e]);
-                  float cdf, xpdf;
-                  gelu_terms(h, cdf, xpdf);
-                  t8[e] = h * cdf;
-                }
-              }
+            for (int c = 0; c < 4; ++c) {
               uint4 pk;
-              pk.x = pack_bf16x2(t8[0], t8[1]); pk.y = pack_bf16x2(t8[2], t8[3]);
-              pk.z = pack_bf16x2(t8[4], t8[5]); pk.w = pack_bf16x2(t8[6], t8[7]);
+              pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+              pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
               *reinterpret_cast<uint4*>(staging_chunk(stg, r, c)) = pk;
             }
           }
@@ -301,7 +349,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           group_bar(1 + grp);
           if (issuer) {
             if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg, nb, m0);
-            else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg, nb, m0);
             else tma_store_2d(&tmD, stg, nb, m0);
             bulk_commit();
           }
@@ -339,7 +386,7 @@ EncodeTiledFn get_encode_tiled() {
 
 // 2-D tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle
 int make_tmap_2d(CUtensorMap* m, bool f32, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                 uint32_t box_outer) {
+                 uint32_t box_outer, bool swizzle64 = false) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -350,7 +397,7 @@ int make_tmap_2d(CUtensorMap* m, bool f32, const void* base, uint64_t inner, uin
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
@@ -431,12 +478,12 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   if (!b_major) e = make_tmap_2d(&tmB, false, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)BN);
   else e = make_tmap_2d(&tmB, false, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
   if (e) return e;
-  // output maps: one [128 rows x 128 bytes] box per staged chunk; the copy engine clips rows >= M and columns >= N
-  e = make_tmap_2d(&tmD, f32_out, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, f32_out ? 32 : 64, GBM);
+  // output maps: one [128 rows x 64 bytes] box per staged chunk; the copy engine clips rows >= M and columns >= N
+  e = make_tmap_2d(&tmD, f32_out, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, f32_out ? 16 : 32, GBM, true);
   if (e) return e;
   tmD2 = tmD;
   if (epilogue == SWINB200_EPI_BIAS_GELU) {
-    e = make_tmap_2d(&tmD2, false, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, GBM);
+    e = make_tmap_2d(&tmD2, false, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 32, GBM, true);
     if (e) return e;
   }
 
