@@ -163,13 +163,21 @@ __global__ void __launch_bounds__(256) ln_residual_fwd_kernel(const T* __restric
   const int nwarps = gridDim.x * warps_per_block;
   const float invC = 1.0f / (float)C;
   for (int row = warp_global; row < rows; row += nwarps) {
-    float v[NCHUNK][8];
+    float v[NCHUNK][8], xi[NCHUNK][8];
     float sum = 0.f;
+    // every global load of the row (branch output and residual stream) is issued before the first reduction
 #pragma unroll
     for (int j = 0; j < NCHUNK; ++j) {
       const int c = lane * 8 + j * 256;
       if (c < C) {
         ld8(z + (size_t)row * C + c, v[j]);
+        if (x_in) ld8(x_in + (size_t)row * C + c, xi[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) sum += v[j][e];
       }
@@ -211,10 +219,8 @@ __global__ void __launch_bounds__(256) ln_residual_fwd_kernel(const T* __restric
           for (int e = 0; e < 8; ++e) r[e] *= sc;
         }
         if (x_in) {
-          float xi[8];
-          ld8(x_in + (size_t)row * C + c, xi);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += xi[e];
+          for (int e = 0; e < 8; ++e) r[e] += xi[j][e];
         }
         st8(x_out + (size_t)row * C + c, r);
         st8(xb_out + (size_t)row * C + c, r);
@@ -228,92 +234,184 @@ __global__ void __launch_bounds__(256) ln_residual_fwd_kernel(const T* __restric
 }
 
 // backward: dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dx*scale*gamma
-// column sums (dgamma, dbeta, dbias_prev) accumulated per lane across the warp's rows, reduced across
-// the block's warps in shared memory, then one fp32 atomic per column per block.
-template <typename T, int NCHUNK>
-__global__ void __launch_bounds__(256) ln_residual_bwd_kernel(const float* __restrict__ dx, const T* __restrict__ z,
-                                                              const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                              const float* __restrict__ sample_scale, T* __restrict__ dz,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float* __restrict__ dbias_prev, int rows, int C,
-                                                              int rows_per_sample) {
-  extern __shared__ float red[];  // [3][C]
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + wib;
-  const int nwarps = gridDim.x * warps_per_block;
+//
+// Persistent CTAs stream row tiles through shared memory with the bulk-copy engine: a tile of TR consecutive rows is one
+// contiguous region of dx (fp32) and of z, so each tile is two cp.async.bulk loads (double-buffered, mbarrier
+// complete_tx) and one cp.async.bulk store of dz -- HBM traffic never waits on the arithmetic.  Per tile:
+//   pass 1 (warp per row)            row means of g and g*xhat via warp shuffles -> shared scalars
+//   pass 2 (thread per 8 channels)   dz rows into the staged output tile; per-channel sums for dgamma / dbeta /
+//                                    dbias_prev stay in 24 registers for the CTA's whole lifetime
+// and one fp32 atomic per channel per thread group at the end.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void lnb_mbar_init(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void lnb_mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lnb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 26)) {
+      printf("swinb200: ln_residual_bwd tile wait timed out (block %d)\n", (int)blockIdx.x);
+      __trap();
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) ln_residual_bwd_kernel(const float* __restrict__ dx, const T* __restrict__ z,
+                                                                 const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ sample_scale, T* __restrict__ dz,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 float* __restrict__ dbias_prev, int rows, int C,
+                                                                 int rows_per_sample, int TR) {
+  extern __shared__ __align__(128) unsigned char lsm[];
+  const size_t dx_bytes = (size_t)TR * C * 4, z_bytes = (size_t)TR * C * sizeof(T);
+  float* dxs[2] = {reinterpret_cast<float*>(lsm), reinterpret_cast<float*>(lsm + dx_bytes)};
+  T* zs[2] = {reinterpret_cast<T*>(lsm + 2 * dx_bytes), reinterpret_cast<T*>(lsm + 2 * dx_bytes + z_bytes)};
+  T* outs[2] = {reinterpret_cast<T*>(lsm + 2 * dx_bytes + 2 * z_bytes), reinterpret_cast<T*>(lsm + 2 * dx_bytes + 3 * z_bytes)};
+  float* rsc = reinterpret_cast<float*>(lsm + 2 * dx_bytes + 4 * z_bytes);   // [TR][4]: rstd*sc?, see below
+  uint64_t* full = reinterpret_cast<uint64_t*>(rsc + TR * 4);                // [2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (rows + TR - 1) / TR;
   const float invC = 1.0f / (float)C;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float a_g[NCHUNK][8], a_b[NCHUNK][8], a_z[NCHUNK][8];
-  float gm[NCHUNK][8];
-#pragma unroll
-  for (int j = 0; j < NCHUNK; ++j) {
-    const int c = lane * 8 + j * 256;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { a_g[j][e] = 0.f; a_b[j][e] = 0.f; a_z[j][e] = 0.f; gm[j][e] = 0.f; }
-    if (c < C) ld8(gamma + c, gm[j]);
-  }
-  for (int row = warp_global; row < rows; row += nwarps) {
-    const float mean = stats[2 * (size_t)row], rstd = stats[2 * (size_t)row + 1];
-    const float sc = sample_scale ? sample_scale[row / rows_per_sample] : 1.0f;
-    float du[NCHUNK][8], xh[NCHUNK][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int c = lane * 8 + j * 256;
-      if (c < C) {
-        float zz[8];
-        ld8(dx + (size_t)row * C + c, du[j]);
-        ld8(z + (size_t)row * C + c, zz);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          du[j][e] *= sc;
-          xh[j][e] = (zz[e] - mean) * rstd;
-          const float g = du[j][e] * gm[j][e];
-          s1 += g;
-          s2 += g * xh[j][e];
-          a_b[j][e] += du[j][e];
-          a_g[j][e] += du[j][e] * xh[j][e];
-        }
-      }
-    }
-    s1 = warp_sum(s1) * invC;
-    s2 = warp_sum(s2) * invC;
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-      const int c = lane * 8 + j * 256;
-      if (c < C) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o[e] = rstd * (du[j][e] * gm[j][e] - s1 - xh[j][e] * s2);
-          // the bias gradient of the preceding Linear sums what that Linear's backward will see,
-          // i.e. the stored (rounded) dz
-          a_z[j][e] += Act<T>::round(o[e]);
-        }
-        st8(dz + (size_t)row * C + c, o);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NCHUNK; ++j) {
-    const int c = lane * 8 + j * 256;
-    if (c < C) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&red[c + e], a_g[j][e]);
-        atomicAdd(&red[C + c + e], a_b[j][e]);
-        atomicAdd(&red[2 * C + c + e], a_z[j][e]);
-      }
-    }
+  const int nchunks = C / 8;
+  const int ngrp = 256 / nchunks > 0 ? 256 / nchunks : 1;    // pass-2 thread groups (each covers all channels)
+  const int grp = tid / nchunks, chunk = tid - grp * nchunks;
+  const bool p2_active = grp < ngrp && nchunks <= 256;
+  const int c2 = chunk * 8;
+
+  if (tid == 0) {
+    lnb_mbar_init(&full[0], 1);
+    lnb_mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[C + i]);
-    if (dbias_prev) atomicAdd(dbias_prev + i, red[2 * C + i]);
+
+  auto issue = [&](int tile, int stage) {
+    const int r0 = tile * TR;
+    const int nr = min(TR, rows - r0);
+    const uint32_t b1 = (uint32_t)((size_t)nr * C * 4), b2 = (uint32_t)((size_t)nr * C * sizeof(T));
+    lnb_mbar_expect(&full[stage], b1 + b2);
+    bulk_load(dxs[stage], dx + (size_t)r0 * C, b1, &full[stage]);
+    bulk_load(zs[stage], z + (size_t)r0 * C, b2, &full[stage]);
+  };
+
+  float gm2[8], a_g[8], a_b[8], a_z[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { gm2[e] = 0.f; a_g[e] = 0.f; a_b[e] = 0.f; a_z[e] = 0.f; }
+  if (p2_active) ld8(gamma + c2, gm2);
+  // pass-1 ownership: lane holds channels lane*8 + 256*j (j < 4) of every row its warp visits
+  float gm1[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gm1[j][e] = 0.f;
+    if (lane * 8 + j * 256 < C) ld8(gamma + lane * 8 + j * 256, gm1[j]);
+  }
+
+  int it = 0;
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int r0 = tile * TR;
+    const int nr = min(TR, rows - r0);
+    if (tid == 0) {
+      const int nxt = tile + gridDim.x;
+      if (nxt < ntiles) issue(nxt, stage ^ 1);     // that stage was fully consumed before the previous iteration's last barrier
+    }
+    const float* dxt = dxs[stage];
+    const T* zt = zs[stage];
+    T* ot = outs[stage];
+    lnb_mbar_wait(&full[stage], (uint32_t)((it >> 1) & 1));
+    // ---- pass 1: row statistics (warp per row): A = sum dx*gamma, Bq = sum dx*gamma*z -------------------------------
+    for (int rr = warp; rr < nr; rr += 8) {
+      const int row = r0 + rr;
+      float A = 0.f, Bq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane * 8 + j * 256;
+        if (c < C) {
+          float d8[8], z8[8];
+          ld8(dxt + (size_t)rr * C + c, d8);
+          ld8(zt + (size_t)rr * C + c, z8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g = d8[e] * gm1[j][e];
+            A += g;
+            Bq = fmaf(g, z8[e], Bq);
+          }
+        }
+      }
+      A = warp_sum(A);
+      Bq = warp_sum(Bq);
+      if (lane == 0) {
+        const float mean = __ldg(stats + 2 * (size_t)row), rstd = __ldg(stats + 2 * (size_t)row + 1);
+        const float sc = sample_scale ? __ldg(sample_scale + row / rows_per_sample) : 1.0f;
+        // mean_c(g) and mean_c(g * xhat) with g = dx*sc*gamma, xhat = (z - mean) * rstd
+        rsc[rr * 4 + 0] = -mean * rstd;                       // xhat = z * rstd + this
+        rsc[rr * 4 + 1] = rstd;
+        rsc[rr * 4 + 2] = sc * A * invC;
+        rsc[rr * 4 + 3] = sc * rstd * (Bq - mean * A) * invC;
+      }
+    }
+    // the output stage written two tiles ago must have been read out by the copy engine
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    // ---- pass 2: dz + per-channel sums (thread per 8 channels) ------------------------------------------------------
+    if (p2_active) {
+      for (int rr = grp; rr < nr; rr += ngrp) {
+        const float4 st = *reinterpret_cast<const float4*>(rsc + rr * 4);
+        const float sc = sample_scale ? __ldg(sample_scale + (r0 + rr) / rows_per_sample) : 1.0f;
+        float d8[8], z8[8], o8[8];
+        ld8(dxt + (size_t)rr * C + c2, d8);
+        ld8(zt + (size_t)rr * C + c2, z8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float du = d8[e] * sc;
+          const float xh = fmaf(z8[e], st.y, st.x);
+          o8[e] = st.y * (fmaf(du, gm2[e], -st.z) - xh * st.w);
+          a_b[e] += du;
+          a_g[e] = fmaf(du, xh, a_g[e]);
+          a_z[e] += o8[e];
+        }
+        st8(ot + (size_t)rr * C + c2, o8);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(dz + (size_t)r0 * C, ot, (uint32_t)((size_t)nr * C * sizeof(T)));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (p2_active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(dgamma + c2 + e, a_g[e]);
+      atomicAdd(dbeta + c2 + e, a_b[e]);
+      if (dbias_prev) atomicAdd(dbias_prev + c2 + e, a_z[e]);
+    }
   }
 }
 
@@ -624,18 +722,26 @@ extern "C" int swinb200_ln_residual_fwd(const void* z, int act_dtype, const floa
 template <typename T>
 static int launch_ln_bwd(const float* dx, const T* z, const float* stats, const float* gamma, const float* ss, T* dz,
                          float* dgamma, float* dbeta, float* dbias_prev, int rows, int C, int rps, cudaStream_t s) {
-  const int blocks = min((rows + 7) / 8, sm_count() * 2);
-  const int nchunk = (C + 255) / 256;
-  const size_t smem = 3 * (size_t)C * sizeof(float);
-#define SWB_LN_BWD(N) ln_residual_bwd_kernel<T, N><<<blocks, 256, smem, s>>>(dx, z, stats, gamma, ss, dz, dgamma, dbeta, dbias_prev, rows, C, rps)
-  switch (nchunk) {
-    case 1: SWB_LN_BWD(1); break;
-    case 2: SWB_LN_BWD(2); break;
-    case 3: SWB_LN_BWD(3); break;
-    case 4: SWB_LN_BWD(4); break;
-    default: set_error("ln_residual_bwd: C=%d > 1024 unsupported", C); return SWINB200_ERR_UNSUPPORTED;
+  if (C / 8 > 256) {
+    set_error("ln_residual_bwd: C=%d > 2048 unsupported", C);
+    return SWINB200_ERR_UNSUPPORTED;
   }
-#undef SWB_LN_BWD
+  // rows per tile: two stages of (dx fp32 + z) plus two output stages within ~100 KB (two CTAs per SM), at most 8
+  const size_t per_row = (size_t)C * (2 * 4 + 4 * sizeof(T));
+  int TR = (int)min((size_t)8, (size_t)(100 * 1024) / per_row);
+  if (TR < 1) {
+    set_error("ln_residual_bwd: C=%d too large for the shared-memory tile", C);
+    return SWINB200_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)TR * per_row + (size_t)TR * 16 + 64;
+  static bool configured = false;
+  if (!configured) {
+    SWB_CUDA(cudaFuncSetAttribute(ln_residual_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  const int ntiles = (rows + TR - 1) / TR;
+  const int blocks = max(1, min(ntiles, 2 * sm_count()));
+  ln_residual_bwd_kernel<T><<<blocks, 256, smem, s>>>(dx, z, stats, gamma, ss, dz, dgamma, dbeta, dbias_prev, rows, C, rps, TR);
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }

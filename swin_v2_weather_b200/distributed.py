@@ -27,6 +27,9 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
+            # NCCL prints its version banner on stdout at INFO/VERSION level; keep stdout for results only
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SWINB200_KEEP_NCCL_DEBUG"):
+                os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend=backend, init_method="env://", rank=rank, world_size=world)
     return rank, world, local
 

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r1_2gpu.json 2> gpurun_out/bench_r1_2gpu.err; echo "bench2 exit $?"; tail -5 gpurun_out/bench_r1_2gpu.err | cut -c1-300; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1_2gpu.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['kernel_families'])"
