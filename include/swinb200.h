@@ -32,6 +32,10 @@ enum {
   SWINB200_EPI_DGELU = 2,     /* D = acc * gelu_erf'(aux)                       (D, aux: act)        */
   SWINB200_EPI_ADD_F32 = 3,   /* D = acc + aux                                  (D, aux: fp32)       */
   SWINB200_EPI_F32 = 4,       /* D = acc  (or D += acc when accumulate != 0)    (D: fp32)            */
+  SWINB200_EPI_BIAS_QKNORM = 5, /* qkv projection: D = acc + bias with N = 3*C packed [q | k | v]; every group of ld_aux
+                                   (= head_dim) columns of the q and k thirds is divided by max(||.||_2, 1e-12)
+                                   (F.normalize, swinv2_global.py:185,304); D2 (M, 2*N/(3*head_dim)) fp32 receives the
+                                   reciprocal norms.  tcgen05 back end, head_dim 96 only.               (D: act)  */
 };
 /* GEMM back ends */
 enum { SWINB200_GEMM_SIMT = 0, SWINB200_GEMM_TCGEN05 = 1 };

@@ -128,7 +128,14 @@ extern "C" int swinb200_gemm(int backend, int M, int N, int K, const void* A, in
   SWB_CHECK_ARG(a_major == 0 || a_major == 1, "gemm: a_major must be 0/1");
   SWB_CHECK_ARG(b_major == 0 || b_major == 1, "gemm: b_major must be 0/1");
   SWB_CHECK_ARG(lda >= (a_major ? M : K) && ldb >= (b_major ? N : K) && ldd >= N, "gemm: leading dimension too small");
-  SWB_CHECK_ARG(epilogue >= SWINB200_EPI_BIAS && epilogue <= SWINB200_EPI_F32, "gemm: unknown epilogue %d", epilogue);
+  SWB_CHECK_ARG(epilogue >= SWINB200_EPI_BIAS && epilogue <= SWINB200_EPI_BIAS_QKNORM, "gemm: unknown epilogue %d", epilogue);
+  if (epilogue == SWINB200_EPI_BIAS_QKNORM) {
+    SWB_CHECK_ARG(backend == SWINB200_GEMM_TCGEN05 && in_dtype == SWINB200_BF16 && out_dtype == SWINB200_BF16,
+                  "gemm: BIAS_QKNORM is a tcgen05 / bf16 epilogue (use BIAS + swinb200_qk_normalize elsewhere)");
+    SWB_CHECK_ARG(D2 != nullptr && ld_aux == 96 && N % 288 == 0 && a_major == 0 && b_major == 0,
+                  "gemm: BIAS_QKNORM needs D2 (inverse norms), head_dim 96 and N = 3*C with C a multiple of 96");
+    return gemm_tcgen05(M, N, K, A, a_major, lda, B, b_major, ldb, epilogue, bias, D, ldd, D2, aux, ld_aux, accumulate, 1, (cudaStream_t)stream);
+  }
   const bool f32_out = (epilogue == SWINB200_EPI_ADD_F32 || epilogue == SWINB200_EPI_F32);
   SWB_CHECK_ARG(out_dtype == (f32_out ? SWINB200_F32 : in_dtype), "gemm: out_dtype %d does not match epilogue %d", out_dtype, epilogue);
   SWB_CHECK_ARG(epilogue != SWINB200_EPI_BIAS_GELU || D2, "gemm: BIAS_GELU needs D2");

@@ -26,6 +26,7 @@ struct GemmTcParams {
   int M, N, K;
   const float* bias;
   const void* aux;
+  float* inv_norm;   // BIAS_QKNORM: (M, 2*N/(3*96)) reciprocal L2 norms of the q / k head vectors
   int ld_aux;
   int atomic_out;  // EPI_F32: 1 = TMA reduce-add (split-K / accumulate), 0 = plain TMA store
   int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
@@ -36,7 +37,7 @@ struct GemmCfg {
   static constexpr int kStageA = GBM * GBK * 2;
   static constexpr int kStageB = BN * GBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kStages = (BN >= 192) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOffStaging = kStages * kStage;
   static constexpr int kOffBars = kOffStaging + 4 * kStagingBytes;
@@ -237,6 +238,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
       // epilogue operand (h for DGELU, the fp32 residual gradient for ADD_F32): 64 bytes per row per chunk, fetched one
       // chunk ahead into registers so its latency hides behind the previous chunk's arithmetic
+      if (EPI == SWINB200_EPI_BIAS_QKNORM) {
+        // one head (96 columns = 3 chunks) per epilogue group: bias, L2 norm over the head, scale, stage, store
+        const int nh0 = n0 + grp * 96;                      // first column of this group's head
+        if (nh0 >= p.N) {                                    // N = 3*C with an odd C/96: the last tile holds one head
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          continue;
+        }
+        const bool normalise = nh0 < (p.N / 3) * 2;          // q and k thirds only
+        float v[96];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          uint32_t rr[32];
+          tmem_ld_32x32(t_row + grp * 96 + q * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[q * 32 + i] = __uint_as_float(rr[i]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 24; ++g) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nh0 + g * 4));
+            v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+          }
+        }
+        if (normalise) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 96; ++i) ss = fmaf(v[i], v[i], ss);
+          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+          for (int i = 0; i < 96; ++i) v[i] *= inv;
+          if (row_ok) p.inv_norm[(size_t)m * ((p.N / 3) * 2 / 96) + nh0 / 96] = inv;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          unsigned char* stg = stg0 + (nstore & 1) * kStagingBytes;
+          ++nstore;
+          if (issuer) bulk_wait_read1();
+          group_bar(1 + grp);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[q * 32 + c * 8 + 0], v[q * 32 + c * 8 + 1]); pk.y = pack_bf16x2(v[q * 32 + c * 8 + 2], v[q * 32 + c * 8 + 3]);
+            pk.z = pack_bf16x2(v[q * 32 + c * 8 + 4], v[q * 32 + c * 8 + 5]); pk.w = pack_bf16x2(v[q * 32 + c * 8 + 6], v[q * 32 + c * 8 + 7]);
+            *reinterpret_cast<uint4*>(staging_chunk(stg, r, c)) = pk;
+          }
+          fence_proxy_async_smem();
+          group_bar(1 + grp);
+          if (issuer) {
+            tma_store_2d(&tmD, stg, nh0 + q * 32, m0);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        continue;
+      }
       uint4 aux_nxt[4];
       auto aux_fetch = [&](int chn) {
         if (kHasAux) {
@@ -450,6 +511,7 @@ static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, c
 int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
                  const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
                  cudaStream_t stream) {
+  const bool qknorm = (epilogue == SWINB200_EPI_BIAS_QKNORM);
   SWB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm(tcgen05): lda/ldb must be multiples of 8 elements (16 bytes)");
   SWB_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "gemm(tcgen05): N and ldd must be multiples of 8");
   SWB_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0), "gemm(tcgen05): operands must be 16-byte aligned");
@@ -457,11 +519,12 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   SWB_CHECK_ARG(D2 == nullptr || ((uintptr_t)D2 % 16 == 0), "gemm(tcgen05): D2 must be 16-byte aligned");
   SWB_CHECK_ARG(bias == nullptr || ((uintptr_t)bias % 16 == 0), "gemm(tcgen05): bias must be 16-byte aligned");
 
-  const int BN = (N > 128) ? 256 : 128;
+  const int BN = qknorm ? 192 : ((N > 128) ? 256 : 128);   // QKNORM: two 96-wide heads per tile
   const bool f32_out = (epilogue == SWINB200_EPI_ADD_F32 || epilogue == SWINB200_EPI_F32);
   GemmTcParams p;
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.inv_norm = qknorm ? reinterpret_cast<float*>(D2) : nullptr;
   p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
   p.num_m_tiles = (M + GBM - 1) / GBM;
   p.num_n_tiles = (N + BN - 1) / BN;
@@ -487,6 +550,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
     if (e) return e;
   }
 
+  if (qknorm) return launch_tc<192, false, false, SWINB200_EPI_BIAS_QKNORM>(tmA, tmB, tmD, tmD2, p, stream);
   if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
   return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
 }

@@ -114,8 +114,7 @@ class SwinBlockFn(torch.autograd.Function):
         scale_c = scale.detach().contiguous()
         bias_c = None if bias is None else bias.detach().contiguous()
         # attention branch
-        qkv = ops.gemm(mode, xb, 0, wq, 0, EPI_BIAS, bias=qkv_b.detach())                       # (T, 3C)
-        inv_norm = ops.qk_normalize_(qkv, C, heads)
+        qkv, inv_norm = ops.qkv_projection(mode, xb, wq, qkv_b.detach(), C, heads)              # (T, 3C): q^, k^, v
         o, lse = ops.window_attn_fwd(qkv, scale_c, bias_c, B, H, W, C, heads, Wh, Ww, s0, s1, mode)
         z1 = ops.gemm(mode, o, 0, wp, 0, EPI_BIAS, bias=proj_b.detach())                         # (T, C)
         x_mid, xb_mid, st1 = ops.ln_residual_fwd(z1, x2, n1_w.detach(), n1_b.detach(), dp1, None, H * W, mode)

@@ -12,8 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (BACKEND_SIMT, BACKEND_TCGEN05, BF16, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_F32, F32,
-                   SwinB200Error)
+from ._lib import (BACKEND_SIMT, BACKEND_TCGEN05, BF16, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_QKNORM, EPI_DGELU,
+                   EPI_F32, F32, SwinB200Error)
 
 LN_EPS = 1e-5
 
@@ -127,6 +127,22 @@ def gemm(mode: ComputeMode, A: torch.Tensor, a_major: int, B: torch.Tensor, b_ma
               _chk(out2, "out2", out_dtype, True), _chk(aux, "aux", None, True), 0 if aux is None else aux.shape[1],
               _code(out_dtype), int(accumulate), int(split_k), _stream())
     return (out, out2) if epilogue == EPI_BIAS_GELU else out
+
+
+def qkv_projection(mode: ComputeMode, xb: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, C: int, heads: int):
+    """qkv = xb @ W^T + b with q and k L2-normalised per head; returns (qkv, inv_norm (T, 2, heads)).
+    tcgen05 / head_dim 96: the normalisation runs in the GEMM epilogue (accumulators never leave fp32 before it);
+    otherwise the GEMM is followed by the stand-alone normalisation kernel."""
+    T = xb.shape[0]
+    if mode.gemm_backend == BACKEND_TCGEN05 and C // heads == 96:
+        qkv = torch.empty((T, 3 * C), dtype=xb.dtype, device=xb.device)
+        inv_norm = torch.empty((T, 2, heads), dtype=torch.float32, device=xb.device)
+        _lib.call("swinb200_gemm", BACKEND_TCGEN05, T, 3 * C, C, _chk(xb, "xb", torch.bfloat16), 0, C, _chk(w, "w", torch.bfloat16), 0, C,
+                  BF16, EPI_BIAS_QKNORM, _chk(bias, "bias", torch.float32), qkv.data_ptr(), 3 * C, inv_norm.data_ptr(), 0, 96, BF16,
+                  0, 1, _stream())
+        return qkv, inv_norm
+    qkv = gemm(mode, xb, 0, w, 0, EPI_BIAS, bias=bias)
+    return qkv, qk_normalize_(qkv, C, heads)
 
 
 def wgrad_split_k(M: int, N: int, K: int) -> int:

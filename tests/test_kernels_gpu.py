@@ -341,6 +341,24 @@ def test_gemm_tcgen05(case):
     run_gemm_case(case, torch.bfloat16, BACKEND_TCGEN05)
 
 
+@pytest.mark.parametrize("T,C,heads", [(700, 768, 8), (333, 192, 2), (260, 96, 1), (129, 288, 3)])
+def test_gemm_tcgen05_qkv_projection_fused_normalise(T, C, heads):
+    x = gen(T, C, seed=50, scale=0.5).to(torch.bfloat16)
+    w = gen(3 * C, C, seed=51, scale=0.05).to(torch.bfloat16)
+    b = gen(3 * C, seed=52)
+    qkv, inv = ops.qkv_projection(ops.MODE_BF16, x, w, b, C, heads)
+    d = C // heads
+    ref = (x.float().double() @ w.float().double().t() + b.double()).float().view(T, 3, heads, d)
+    nrm = ref[:, :2].norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    want = ref.clone()
+    want[:, :2] = ref[:, :2] / nrm
+    assert rel(qkv.view(T, 3, heads, d), want) < 4e-3          # bf16 storage of unit vectors / v
+    assert rel(inv, 1.0 / nrm.squeeze(-1)) < 1e-5
+    # and it agrees with the unfused path (GEMM + stand-alone normalisation kernel)
+    qkv2, inv2 = ops.qkv_projection(ops.MODE_BF16_SIMT, x, w, b, C, heads)
+    assert rel(qkv, qkv2) < 6e-3 and rel(inv, inv2) < 3e-3
+
+
 @pytest.mark.parametrize("split_k", [2, 5, 16])
 def test_gemm_tcgen05_split_k(split_k):
     run_gemm_case((768, 3072, 4000, 1, 1, EPI_F32), torch.bfloat16, BACKEND_TCGEN05, split_k)
