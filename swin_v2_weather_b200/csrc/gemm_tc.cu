@@ -1,10 +1,10 @@
 // tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulation in TMEM.
 //
-// Persistent, warp-specialised, one CTA per SM (320 threads):
+// Persistent, warp-specialised, one CTA per SM (576 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one thread: tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
-//   warps 2..9  epilogue       (two groups of 4 warps; each group owns every other 64-byte column chunk of the tile:
-//                               tcgen05.ld -> fused epilogue in registers -> swizzled, double-buffered smem staging -> TMA store /
+//   warps 2..17 epilogue       (four groups of 4 warps; group g owns every fourth 64-byte column chunk of the tile:
+//                               tcgen05.ld -> fused epilogue in registers -> swizzled smem staging -> TMA store /
 //                               TMA reduce-add, so global writes are whole 64-byte row pieces issued by the copy engine)
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
@@ -19,8 +19,9 @@ using namespace ptx;
 
 constexpr int GBM = 128;  // UMMA M (cta_group::1)
 constexpr int GBK = 64;   // k per pipeline stage (one 128-byte swizzle row of bf16)
-constexpr int kGemmThreads = 320;
-constexpr int kStagingBytes = 128 * 64;    // one [128 rows x 64 B] output chunk; two per epilogue group (double-buffered)
+constexpr int kEpiGroups = 4;             // epilogue groups of 4 warps (one warp per TMEM lane quarter)
+constexpr int kGemmThreads = 64 + kEpiGroups * 128;
+constexpr int kStagingBytes = 128 * 64;    // one [128 rows x 64 B] output chunk per epilogue group
 
 struct GemmTcParams {
   int M, N, K;
@@ -40,7 +41,7 @@ struct GemmCfg {
   static constexpr int kStages = (BN >= 192) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOffStaging = kStages * kStage;
-  static constexpr int kOffBars = kOffStaging + 4 * kStagingBytes;
+  static constexpr int kOffBars = kOffStaging + kEpiGroups * kStagingBytes;
   static constexpr int kSmem = kOffBars + 256 + 1024 /* alignment slack */;
 };
 
@@ -129,7 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);
+      mbar_init(&tempty_bar[b], 4 * kEpiGroups);
     }
     fence_barrier_init();
   }
@@ -217,14 +218,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================================= epilogue ===================================
-    const int ew = warp - 2;               // 0..7
-    const int grp = ew >> 2;               // epilogue group: owns chunks grp, grp+2, ...
+    const int ew = warp - 2;               // 0 .. 4*kEpiGroups-1
+    const int grp = ew >> 2;               // epilogue group: owns chunks grp, grp + kEpiGroups, ...
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;     // row inside the tile
     const bool issuer = (ew & 3) == 0 && lane == 0;
-    unsigned char* stg0 = smem + Cfg::kOffStaging + grp * 2 * kStagingBytes;   // two staging buffers per group
+    unsigned char* stg0 = smem + Cfg::kOffStaging + grp * kStagingBytes;       // one staging buffer per group
     int local = 0;
-    uint32_t nstore = 0;                   // chunks staged so far by this group (selects the staging buffer)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int rest = tile / p.split_k;
       const int n0 = (rest % p.num_n_tiles) * BN;
@@ -239,9 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // epilogue operand (h for DGELU, the fp32 residual gradient for ADD_F32): 64 bytes per row per chunk, fetched one
       // chunk ahead into registers so its latency hides behind the previous chunk's arithmetic
       if (EPI == SWINB200_EPI_BIAS_QKNORM) {
-        // one head (96 columns = 3 chunks) per epilogue group: bias, L2 norm over the head, scale, stage, store
+        // one head (96 columns = 3 chunks) per epilogue group (groups 0 and 1; the MMA bounds this GEMM):
+        // bias, L2 norm over the head, scale, stage, store
         const int nh0 = n0 + grp * 96;                      // first column of this group's head
-        if (nh0 >= p.N) {                                    // N = 3*C with an odd C/96: the last tile holds one head
+        if (grp >= 2 || nh0 >= p.N) {                        // idle groups / odd C/96: the last tile holds one head
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
@@ -275,9 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          unsigned char* stg = stg0 + (nstore & 1) * kStagingBytes;
-          ++nstore;
-          if (issuer) bulk_wait_read1();
+          unsigned char* stg = stg0;
+          if (issuer) bulk_wait_read0();
           group_bar(1 + grp);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -312,14 +312,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       aux_fetch(grp);
 #pragma unroll 1
-      for (int ch = grp; ch < kNumChunks; ch += 2) {
+      for (int ch = grp; ch < kNumChunks; ch += kEpiGroups) {
         const int nb = n0 + ch * kChunkCols;
         if (nb >= p.N) break;                       // whole chunk beyond N (uniform across the group)
         uint4 aux_cur[4];
         if (kHasAux) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) aux_cur[q] = aux_nxt[q];
-          aux_fetch(ch + 2);
+          aux_fetch(ch + kEpiGroups);
         }
         float v[kChunkCols];
         if (kChunkCols == 32) {
@@ -360,57 +360,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[g * 4 + 2] += __uint_as_float(aux_cur[g].z); v[g * 4 + 3] += __uint_as_float(aux_cur[g].w);
           }
         }
-        // ---- stage the chunk and hand it to the copy engine.  Staging is double-buffered: the store issued two chunks
-        //      ago must have finished *reading* its buffer; GELU stages the pre-activation and the activation at once.
-        if (EPI == SWINB200_EPI_BIAS_GELU) {
+        // ---- stage the chunk and hand it to the copy engine: the group's previous store must have finished *reading*
+        //      the staging buffer; with four groups in flight that wait overlaps the other groups' arithmetic.
+        //      GELU stages the pre-activation first, then the activation.
+        constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
           if (issuer) bulk_wait_read0();
-          group_bar(1 + grp);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h
-            uint4 ph, pg;
-            ph.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); ph.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-            ph.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); ph.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-            float h8[8];
-            unpack_bf16x2(ph.x, h8[0], h8[1]); unpack_bf16x2(ph.y, h8[2], h8[3]);
-            unpack_bf16x2(ph.z, h8[4], h8[5]); unpack_bf16x2(ph.w, h8[6], h8[7]);
-            float g8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g8[e] = gelu_fast(h8[e]);
-            pg.x = pack_bf16x2(g8[0], g8[1]); pg.y = pack_bf16x2(g8[2], g8[3]); pg.z = pack_bf16x2(g8[4], g8[5]); pg.w = pack_bf16x2(g8[6], g8[7]);
-            *reinterpret_cast<uint4*>(staging_chunk(stg0, r, c)) = ph;
-            *reinterpret_cast<uint4*>(staging_chunk(stg0 + kStagingBytes, r, c)) = pg;
-          }
-          fence_proxy_async_smem();
-          group_bar(1 + grp);
-          if (issuer) {
-            tma_store_2d(&tmD2, stg0, nb, m0);
-            tma_store_2d(&tmD, stg0 + kStagingBytes, nb, m0);
-            bulk_commit();
-          }
-        } else {
-          unsigned char* stg = stg0 + (nstore & 1) * kStagingBytes;
-          ++nstore;
-          if (issuer) bulk_wait_read1();
           group_bar(1 + grp);
           if (kF32Out) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<float4*>(staging_chunk(stg, r, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+              *reinterpret_cast<float4*>(staging_chunk(stg0, r, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint4 pk;
               pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
               pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-              *reinterpret_cast<uint4*>(staging_chunk(stg, r, c)) = pk;
+              *reinterpret_cast<uint4*>(staging_chunk(stg0, r, c)) = pk;
+              if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) {
+                // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h;
+                // v[] is overwritten with the activation for the second pass
+                float h8[8];
+                unpack_bf16x2(pk.x, h8[0], h8[1]); unpack_bf16x2(pk.y, h8[2], h8[3]);
+                unpack_bf16x2(pk.z, h8[4], h8[5]); unpack_bf16x2(pk.w, h8[6], h8[7]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[c * 8 + e] = gelu_fast(h8[e]);
+              }
             }
           }
           fence_proxy_async_smem();
           group_bar(1 + grp);
           if (issuer) {
-            if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg, nb, m0);
-            else tma_store_2d(&tmD, stg, nb, m0);
+            if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg0, nb, m0);
+            else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg0, nb, m0);
+            else tma_store_2d(&tmD, stg0, nb, m0);
             bulk_commit();
           }
         }

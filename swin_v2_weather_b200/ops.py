@@ -146,11 +146,20 @@ def qkv_projection(mode: ComputeMode, xb: torch.Tensor, w: torch.Tensor, bias: t
 
 
 def wgrad_split_k(M: int, N: int, K: int) -> int:
-    """Split-K factor so a weight-gradient GEMM (few output tiles, K = tokens) fills the 148 SMs."""
+    """Split-K factor for a weight-gradient GEMM (few 128x256 output tiles, K = tokens): the smallest split in
+    [2, 16] whose tile x split count fills whole waves of the persistent grid best (>= 95 % of the last wave),
+    so the 148 SMs neither idle in a ragged tail nor pay for more fp32 reduce-add traffic than needed."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
     sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     kb = (K + 63) // 64
-    best = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
+    best, best_eff = 1, 0.0
+    for s in range(1, min(16, kb) + 1):
+        items = tiles * s
+        eff = items / (((items + sms - 1) // sms) * sms)
+        if items >= sms and eff >= 0.95:
+            return s
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
     return best
 
 
