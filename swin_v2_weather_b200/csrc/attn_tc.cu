@@ -13,6 +13,7 @@
 //
 // forward:   S = Q^ K^T (tcgen05, TMEM) -> thread-per-row softmax(scale*S + bias + mask) -> P (bf16, smem)
 //            -> O = P V (tcgen05, accumulator aliases S) -> O / rowsum -> scatter to (T, C); row LSE saved.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -351,6 +352,273 @@ attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// forward, version 2: two CTAs per SM, operands that are only ever the A side of an MMA live in tensor memory
+// ------------------------------------------------------------------------------------------------------------
+// One 128-thread CTA per (sample, window, head); the block scheduler keeps two of them resident per SM so one CTA's
+// gather overlaps the other's softmax / MMAs.  Shared memory holds only K^ and V (B operands) plus one row-major
+// staging tile: Q^ rows land there (coalesced cp.async), are copied by their owning thread into tensor memory
+// (tcgen05.st, thread = row = TMEM lane) and S = Q^ K^T runs with A from TMEM.  P overwrites S in place as packed
+// bf16 (the thread that reads a row's S is the one that writes its P), O = P V again takes A from TMEM, and the
+// staging tile is reused to park the output rows for whole-row global stores.
+//   TMEM columns (256 allocated):  Q^ [0,48)   S [48,224)   P [48,136) in place   O [136,232) over the tail of S
+template <int D>
+struct Fwd2Smem {
+  static constexpr int kChunks = D / 8;
+  static constexpr int kCS = kMaxLP * 16 + 16;
+  static constexpr int kTile = kChunks * kCS;
+  static constexpr int kOffK = 0, kOffV = kTile;
+  static constexpr int kOffStage = 2 * kTile;                    // [128 rows][kRowPitch]
+  static constexpr int kOffTok = kOffStage + 128 * kRowPitch;
+  static constexpr int kOffBar = kOffTok + kMaxLP * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 2)
+attn_tc_fwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ scale_p, const float* __restrict__ bias,
+                    __nv_bfloat16* __restrict__ o, float* __restrict__ lse, const AttnGeom g) {
+  using SM = Fwd2Smem<D>;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr uint32_t kColQ = 0, kColS = 48, kColO = 136;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sK = smem + SM::kOffK;
+  unsigned char* sV = smem + SM::kOffV;
+  unsigned char* sStage = smem + SM::kOffStage;
+  int* tok = reinterpret_cast<int*>(smem + SM::kOffTok);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  SWB_STAMP(0);
+  const int head = blockIdx.x % g.heads;
+  const int w = (blockIdx.x / g.heads) % g.nW;
+  const int b = blockIdx.x / (g.heads * g.nW);
+  const int L = g.L, LP = g.LP;
+  const int ntiles = (L > 128) ? 2 : 1;
+  int label_split = LP;
+  if ((g.s0 > 0) || (g.s1 > 0)) {
+    const int wh = w / g.nWw;
+    if (g.s0 > 0) {
+      const int first_row = g.H - g.s0 - wh * g.Wh;
+      label_split = first_row <= 0 ? 0 : (first_row >= g.Wh ? LP : first_row * g.Ww);
+    } else {
+      label_split = 0;
+    }
+  }
+  const bool plain = (bias == nullptr) && !(label_split > 0 && label_split < L);
+
+  for (int n = tid; n < LP; n += 128) {
+    int rr;
+    tok[n] = (n < L) ? win_token(g, b, w, n, rr) : -1;
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  for (int i = tid; i < (LP - L) * SM::kChunks * 2; i += 128) {          // zero pad rows [L, LP) of K^ and V
+    const int op = i / ((LP - L) * SM::kChunks);
+    const int rem = i - op * (LP - L) * SM::kChunks;
+    const int c = rem / (LP - L), r = L + rem % (LP - L);
+    *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  SWB_STAMP(1);
+
+  const int C3 = 3 * g.C;
+  auto gather_q_tile = [&](int t) {          // Q^ rows of tile t -> staging, row-major, coalesced
+    const int rows = min(128, L - t * 128);
+    for (int i = tid; i < rows * SM::kChunks; i += 128) {
+      const int rr = i / SM::kChunks, c = i - rr * SM::kChunks;
+      cp_async16(sStage + rr * kRowPitch + c * 16, qkv + (size_t)tok[t * 128 + rr] * C3 + head * D + c * 8);
+    }
+  };
+  {
+    const int per_op = L * SM::kChunks;
+    for (int i = tid; i < 2 * per_op; i += 128) {                          // K^ and V -> chunked operand layout
+      const int op = i / per_op;
+      const int rem = i - op * per_op;
+      const int n = rem / SM::kChunks, c = rem - n * SM::kChunks;
+      cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, qkv + (size_t)tok[n] * C3 + (op + 1) * g.C + head * D + c * 8);
+    }
+    gather_q_tile(0);
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  SWB_STAMP(2);
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const float scale_l2 = scale_p[head] * kLog2e;
+  const uint32_t k0 = smem_u32(sK), v0 = smem_u32(sV);
+  const uint32_t idesc_s = umma_idesc_bf16(128, LP, false, false);
+  const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+  uint32_t parity = 0;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int n = t * 128 + tid;                  // this thread's query slot; TMEM lane = tid
+    const bool row_ok = n < L;
+    // ---- Q^ row: staging -> tensor memory (packed bf16, 4 columns per 16-byte chunk) ---------------------------------
+    if (t > 0) {
+      gather_q_tile(t);
+      cp_async_wait_all();
+      __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < SM::kChunks; ++c) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row_ok) v = *reinterpret_cast<const uint4*>(sStage + tid * kRowPitch + c * 16);
+      tmem_st_32x4(t_lane + kColQ + c * 4, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- S = Q^ K^T (A from TMEM) -----------------------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16_ts(tmem_base + kColS, tmem_base + kColQ + k * 8, umma_desc_nosw(k0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 700 + t);
+    parity ^= 1;
+    SWB_STAMP(3);
+    tc_fence_after();
+    // ---- softmax, P written over S in place --------------------------------------------------------------------------------
+    float row_sum = 0.f, row_max = -INFINITY;
+    const uint32_t t_s = t_lane + kColS;
+    if (plain) {
+      uint32_t va[16], vb[16];
+      float mx = -INFINITY;
+      tmem_ld_32x16(t_s, va);
+      for (int c0 = 0; c0 < LP; c0 += 32) {
+        tmem_ld_wait();
+        const bool has_b = c0 + 16 < LP;
+        if (has_b) tmem_ld_32x16(t_s + c0 + 16, vb);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, as_f(va[j]));
+        if (has_b) {
+          tmem_ld_wait();
+          if (c0 + 32 < LP) tmem_ld_32x16(t_s + c0 + 32, va);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, as_f(vb[j]));
+        }
+      }
+      row_max = mx * scale_l2;
+      const float neg_m = -row_max;
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_s + c0, v);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(as_f(v[j]), scale_l2, neg_m));
+        if (c0 + 16 > L) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j >= L) p[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) row_sum += p[j];
+        tmem_st_32x8(t_s + c0 / 2, pack8(p, 0), pack8(p, 8));      // keys [c0, c0+16) -> 8 packed columns, already consumed
+      }
+    } else {
+      const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+      const int my_label = (n >= label_split) ? 1 : 0;
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_s + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int key = c0 + j;
+          float sv = as_f(v[j]) * scale_l2;
+          if (brow != nullptr && key < L) sv += brow[key] * kLog2e;
+          if (((key >= label_split) ? 1 : 0) != my_label) sv += -100.0f * kLog2e;
+          if (key < L) row_max = fmaxf(row_max, sv);
+        }
+      }
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_s + c0, v);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int key = c0 + j;
+          float sv = as_f(v[j]) * scale_l2;
+          if (brow != nullptr && key < L) sv += brow[key] * kLog2e;
+          if (((key >= label_split) ? 1 : 0) != my_label) sv += -100.0f * kLog2e;
+          p[j] = (key < L && row_ok) ? ex2_approx(sv - row_max) : 0.f;
+          row_sum += p[j];
+        }
+        tmem_st_32x8(t_s + c0 / 2, pack8(p, 0), pack8(p, 8));
+      }
+    }
+    if (row_ok)
+      lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] = (row_max + log2f(row_sum)) * 0.6931471805599453f;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    SWB_STAMP(4);
+    // ---- O = P V (A = P from TMEM, B = V read n-major) ------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < LP / 16; ++k)
+        umma_bf16_ts(tmem_base + kColO, tmem_base + kColS + k * 8, umma_desc_nosw(v0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 710 + t);
+    parity ^= 1;
+    SWB_STAMP(5);
+    tc_fence_after();
+    {
+      const float inv = 1.0f / row_sum;
+      float ov[D];
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + kColO + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ov[c0 + j] = as_f(v[j]) * inv;
+      }
+      if (row_ok) park_row<D>(sStage, tid, ov);     // the staging tile is free again: Q^ went to TMEM long ago
+    }
+    tc_fence_before();
+    __syncthreads();
+    scatter_rows<D>(sStage, min(128, L - t * 128), tok, t * 128, o, g.C, head * D, tid, 128);
+    __syncthreads();
+    SWB_STAMP(6);
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 int attn_set_phase_buffer(long long* buf) {
   SWB_CUDA(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
   return SWINB200_OK;
@@ -377,14 +645,30 @@ int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, voi
                      int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
   AttnGeom g;
   if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
-  using SM = FwdSmem<96>;
-  static bool configured = false;
-  if (!configured) {
-    SWB_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("SWINB200_ATTN_FWD");
+    variant = e ? atoi(e) : 2;
   }
-  attn_tc_fwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>((const __nv_bfloat16*)qkv, scale, bias, (__nv_bfloat16*)o,
-                                                                        lse, g);
+  if (variant == 1) {
+    using SM = FwdSmem<96>;
+    static bool configured = false;
+    if (!configured) {
+      SWB_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+      configured = true;
+    }
+    attn_tc_fwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>((const __nv_bfloat16*)qkv, scale, bias,
+                                                                          (__nv_bfloat16*)o, lse, g);
+  } else {
+    using SM = Fwd2Smem<96>;
+    static bool configured = false;
+    if (!configured) {
+      SWB_CUDA(cudaFuncSetAttribute(attn_tc_fwd2_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+      configured = true;
+    }
+    attn_tc_fwd2_kernel<96><<<B * g.nW * heads, 128, SM::kBytes, stream>>>((const __nv_bfloat16*)qkv, scale, bias,
+                                                                           (__nv_bfloat16*)o, lse, g);
+  }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }

@@ -10,6 +10,7 @@
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
 // token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,6 +30,7 @@ struct GemmTcParams {
   const void* aux;
   float* inv_norm;   // BIAS_QKNORM: (M, 2*N/(3*96)) reciprocal L2 norms of the q / k head vectors
   int ld_aux;
+  int debug;       // bring-up timing experiments (SWINB200_GEMM_DEBUG): 1 = no staging wait, 2 = no store, 4 = no tmem ld wait
   int atomic_out;  // EPI_F32: 1 = TMA reduce-add (split-K / accumulate), 0 = plain TMA store
   int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
 };
@@ -366,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          if (issuer) bulk_wait_read0();
+          if (issuer && !(p.debug & 1)) bulk_wait_read0();
           group_bar(1 + grp);
           if (kF32Out) {
 #pragma unroll
@@ -392,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_proxy_async_smem();
           group_bar(1 + grp);
-          if (issuer) {
+          if (issuer && !(p.debug & 2)) {
             if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg0, nb, m0);
             else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg0, nb, m0);
             else tma_store_2d(&tmD, stg0, nb, m0);
@@ -509,6 +511,11 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   GemmTcParams p;
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("SWINB200_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.inv_norm = qknorm ? reinterpret_cast<float*>(D2) : nullptr;
   p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
   p.num_m_tiles = (M + GBM - 1) / GBM;
