@@ -30,17 +30,21 @@ struct GemmTcParams {
   const void* aux;
   float* inv_norm;   // BIAS_QKNORM: (M, 2*N/(3*96)) reciprocal L2 norms of the q / k head vectors
   int ld_aux;
+  int pair;        // 1 = CTA-pair (cta_group::2) launch: 256 x 256 tiles over two SMs
   int debug;       // bring-up timing experiments (SWINB200_GEMM_DEBUG): 1 = no staging wait, 2 = no store, 4 = no tmem ld wait
   int atomic_out;  // EPI_F32: 1 = TMA reduce-add (split-K / accumulate), 0 = plain TMA store
   int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster (two SMs) share one 256 x BN tile: tcgen05.mma.cta_group::2 reads the A rows and one half
+// of the B columns from each CTA's shared memory, so every SM stages (and the tensor core re-reads) a third less operand
+// data per k-step and the smem ring gets deeper.
+template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int kStageA = GBM * GBK * 2;
-  static constexpr int kStageB = BN * GBK * 2;
+  static constexpr int kStageB = (PAIR ? BN / 2 : BN) * GBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN >= 192) ? 4 : 6;
+  static constexpr int kStages = PAIR ? 6 : ((BN >= 192) ? 4 : 6);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOffStaging = kStages * kStage;
   static constexpr int kOffBars = kOffStaging + kEpiGroups * kStagingBytes;
@@ -95,17 +99,65 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+// ---- cta_group::2 (CTA pair) forms.  Shared-window addresses of the two CTAs of a pair differ in bit 24; clearing it
+// addresses the leader (even) CTA's copy of the same variable (CUTLASS: Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one warp in each CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // 16-byte chunk `c` (0..3) of the 64-byte staging row `r`, 64B-swizzled exactly as the TMA store expects
 // (address bits [4,6) ^= bits [7,9)); eight consecutive rows land in eight distinct 16-byte bank groups.
 __device__ __forceinline__ unsigned char* staging_chunk(unsigned char* buf, int r, int c) {
   return buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmTcParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  constexpr int BNL = PAIR ? BN / 2 : BN;              // B columns staged by this CTA
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u; // 0 = leader (issues the MMAs), 1 = peer
+  const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // persistent stride in tiles
+  const int cta_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   constexpr bool kF32Out = (EPI == SWINB200_EPI_ADD_F32 || EPI == SWINB200_EPI_F32);
   constexpr int kChunkCols = kF32Out ? 16 : 32;          // 64 bytes of output per row per chunk
   constexpr int kNumChunks = BN / kChunkCols;
@@ -132,13 +184,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4 * kEpiGroups);
+      mbar_init(&tempty_bar[b], (PAIR ? 2 : 1) * 4 * kEpiGroups);   // PAIR: both CTAs' epilogue warps report to the leader
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -149,48 +205,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // =============================== TMA producer ===============================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
         const int ks = tile % p.split_k;
         const int rest = tile / p.split_k;
-        const int n0 = (rest % p.num_n_tiles) * BN;
-        const int m0 = (rest / p.num_n_tiles) * GBM;
+        const int n0 = (rest % p.num_n_tiles) * BN + (int)crank * BNL;            // PAIR: this CTA's half of the B columns
+        const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           unsigned char* sa = smem + stage * Cfg::kStage;
           unsigned char* sb = sa + Cfg::kStageA;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          // PAIR: every load of both CTAs completes on the leader's barrier, which expects both CTAs' bytes
+          if (!PAIR) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          else if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
           const int k0 = kb * GBK;
+          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+            if (PAIR) tma_load_2d_pair(dst, tm, &full_bar[stage], c0, c1);
+            else tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+            load(sa, &tmA, k0, m0);  // box {64 k, 128 m}
           } else {
 #pragma unroll
             for (int c = 0; c < GBM / 64; ++c)  // box {64 m, 64 k}
-              tma_load_2d(sa + c * (64 * GBK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0);
+              load(sa + c * (64 * GBK * 2), &tmA, m0 + c * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+            load(sb, &tmB, k0, n0);  // box {64 k, BNL n}
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)  // box {64 n, 64 k}
-              tma_load_2d(sb + c * (64 * GBK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0);
+            for (int c = 0; c < BNL / 64; ++c)  // box {64 n, 64 k}
+              load(sb + c * (64 * GBK * 2), &tmB, n0 + c * 64, k0);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // =============================== MMA issuer =================================
-      constexpr uint32_t idesc = umma_idesc_bf16(GBM, BN, A_MN, B_MN);
+    if (lane == 0 && crank == 0) {
+      // =============================== MMA issuer (leader CTA only in PAIR mode) =================================
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GBM : GBM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart, k advances 32 B inside the swizzle row.
       // MN-major: 8-k groups 1024 B apart, 64-wide m/n chunks 64*128 B apart, k advances 16 rows = 2048 B.
       constexpr uint32_t kLboMn = 64 * GBK * 2;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++local) {
         const int ks = tile % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -210,12 +272,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, kLboMn, 1024)
                                         : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_ss_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (PAIR) umma_commit_pair(&tfull_bar[buf]); else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
@@ -227,10 +292,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (ew & 3) == 0 && lane == 0;
     unsigned char* stg0 = smem + Cfg::kOffStaging + grp * kStagingBytes;       // one staging buffer per group
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++local) {
       const int rest = tile / p.split_k;
       const int n0 = (rest % p.num_n_tiles) * BN;
-      const int m0 = (rest / p.num_n_tiles) * GBM;
+      const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
       const int buf = local & 1;
       const uint32_t use = (uint32_t)(local >> 1);
       mbar_wait(&tfull_bar[buf], use & 1, 400 + buf);
@@ -247,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (grp >= 2 || nh0 >= p.N) {                        // idle groups / odd C/96: the last tile holds one head
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
           continue;
         }
         const bool normalise = nh0 < (p.N / 3) * 2;          // q and k thirds only
@@ -297,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
         continue;
       }
       uint4 aux_nxt[4];
@@ -404,16 +469,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
     }
     if (issuer) bulk_wait0();   // all global writes of this CTA have completed before it exits
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA leaves (or frees tensor memory) while its peer can still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -455,21 +522,47 @@ int make_tmap_2d(CUtensorMap* m, bool f32, const void* base, uint64_t inner, uin
   return SWINB200_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
-                     const GemmTcParams& p, cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
+static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
+                          const GemmTcParams& p, cudaStream_t s) {
+  using Cfg = GemmCfg<BN, PAIR>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, PAIR>;
   static bool configured = false;
   if (!configured) {
     SWB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
-  const int grid = min(tiles, sm_count());
-  kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, tmD, tmD2, p);
+  if (!PAIR) {
+    const int grid = min(tiles, sm_count());
+    kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, tmD, tmD2, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * min(tiles, sm_count() / 2));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SWB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmD2, p));
+  }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
+}
+
+// p.num_m_tiles counts 128-row tiles for single-CTA launches and 256-row pair tiles for PAIR launches
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
+                     const GemmTcParams& p, cudaStream_t s) {
+  if (p.pair) {
+    if constexpr (BN == 256) return launch_tc_impl<BN, A_MN, B_MN, EPI, true>(tmA, tmB, tmD, tmD2, p, s);
+  }
+  return launch_tc_impl<BN, A_MN, B_MN, EPI, false>(tmA, tmB, tmD, tmD2, p, s);
 }
 
 // Only the operand-major / epilogue pairs the model uses are instantiated:
@@ -518,7 +611,12 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   }
   p.inv_norm = qknorm ? reinterpret_cast<float*>(D2) : nullptr;
   p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
-  p.num_m_tiles = (M + GBM - 1) / GBM;
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("SWINB200_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+    p.pair = (pair_env && BN == 256 && !qknorm) ? 1 : 0;
+  }
+  p.num_m_tiles = p.pair ? (M + 2 * GBM - 1) / (2 * GBM) : (M + GBM - 1) / GBM;
   p.num_n_tiles = (N + BN - 1) / BN;
   p.kb_total = (K + GBK - 1) / GBK;
   split_k = max(1, min(split_k, p.kb_total));
@@ -530,7 +628,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   if (!a_major) e = make_tmap_2d(&tmA, false, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GBK, GBM);
   else e = make_tmap_2d(&tmA, false, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GBK);
   if (e) return e;
-  if (!b_major) e = make_tmap_2d(&tmB, false, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)BN);
+  if (!b_major) e = make_tmap_2d(&tmB, false, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)(p.pair ? BN / 2 : BN));
   else e = make_tmap_2d(&tmB, false, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
   if (e) return e;
   // output maps: one [128 rows x 64 bytes] box per staged chunk; the copy engine clips rows >= M and columns >= N
@@ -542,7 +640,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
     if (e) return e;
   }
 
-  if (qknorm) return launch_tc<192, false, false, SWINB200_EPI_BIAS_QKNORM>(tmA, tmB, tmD, tmD2, p, stream);
+  if (qknorm) return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, false>(tmA, tmB, tmD, tmD2, p, stream);
   if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
   return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
 }
