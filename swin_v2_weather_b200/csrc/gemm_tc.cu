@@ -614,7 +614,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   {
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("SWINB200_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
-    p.pair = (pair_env && BN == 256 && !qknorm) ? 1 : 0;
+    p.pair = (pair_env && (BN == 256 || BN == 192)) ? 1 : 0;
   }
   p.num_m_tiles = p.pair ? (M + 2 * GBM - 1) / (2 * GBM) : (M + GBM - 1) / GBM;
   p.num_n_tiles = (N + BN - 1) / BN;
@@ -640,7 +640,10 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
     if (e) return e;
   }
 
-  if (qknorm) return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, false>(tmA, tmB, tmD, tmD2, p, stream);
+  if (qknorm) {
+    if (p.pair) return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, true>(tmA, tmB, tmD, tmD2, p, stream);
+    return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, false>(tmA, tmB, tmD, tmD2, p, stream);
+  }
   if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
   return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
 }
