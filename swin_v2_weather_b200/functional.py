@@ -142,28 +142,38 @@ class SwinBlockFn(torch.autograd.Function):
         w1, w2 = SHADOWS.get(fc1_w, mode), SHADOWS.get(fc2_w, mode)
         dx_out = dx_out.contiguous().view(T, C)
 
-        def wgrad(dy, act_in, n_out, n_in):
-            dw = torch.zeros((n_out, n_in), dtype=torch.float32, device=dev)
+        # every fp32 accumulator of this block's backward (split-K weight gradients, column sums, d logit-scale) lives in
+        # one buffer cleared by a single fill instead of ~10 small ones
+        sizes = dict(w_qkv=3 * C * C, w_proj=C * C, w_fc1=hid * C, w_fc2=C * hid, ln2=3 * C, ln1=3 * C, b_fc1=hid,
+                     b_qkv=3 * C, dscale=heads)
+        flat = torch.zeros((sum(-(-v // 64) * 64 for v in sizes.values()),), dtype=torch.float32, device=dev)
+        acc, off = {}, 0
+        for k, v in sizes.items():
+            acc[k] = flat[off:off + v]
+            off += -(-v // 64) * 64          # 256-byte aligned slices (TMA reduce-add needs 16 B)
+
+        def wgrad(dy, act_in, n_out, n_in, key):
+            dw = acc[key].view(n_out, n_in)
             ops.gemm(mode, dy, 1, act_in, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(n_out, n_in, T))
             return dw
 
         # ---- MLP branch: x_out = x_mid + dp2 * LN2(fc2(gelu(fc1(xb_mid))))
-        dz2, dg2, db2, dbias_fc2 = ops.ln_residual_bwd(dx_out, z2, st2, n2_w.detach(), dp2, H * W, mode)
+        dz2, dg2, db2, dbias_fc2 = ops.ln_residual_bwd(dx_out, z2, st2, n2_w.detach(), dp2, H * W, mode, acc=acc["ln2"].view(3, C))
         dh = ops.gemm(mode, dz2, 0, w2, 1, EPI_DGELU, aux=h)                                     # (T, hidden)
-        dw_fc2 = wgrad(dz2, g, C, hid)
-        dbias_fc1 = ops.colsum(dh)
+        dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
+        dbias_fc1 = ops.colsum(dh, out=acc["b_fc1"])
         dx_mid = ops.gemm(mode, dh, 0, w1, 1, EPI_ADD_F32, aux=dx_out)                           # fp32 (T, C)
-        dw_fc1 = wgrad(dh, xb_mid, hid, C)
+        dw_fc1 = wgrad(dh, xb_mid, hid, C, "w_fc1")
         del dh
         # ---- attention branch: x_mid = x + dp1 * LN1(proj(attn(qkv(xb))))
-        dz1, dg1, db1, dbias_proj = ops.ln_residual_bwd(dx_mid, z1, st1, n1_w.detach(), dp1, H * W, mode)
+        dz1, dg1, db1, dbias_proj = ops.ln_residual_bwd(dx_mid, z1, st1, n1_w.detach(), dp1, H * W, mode, acc=acc["ln1"].view(3, C))
         d_o = ops.gemm(mode, dz1, 0, wp, 1, EPI_BIAS)                                            # (T, C)
-        dw_proj = wgrad(dz1, o, C, C)
+        dw_proj = wgrad(dz1, o, C, C, "w_proj")
         dqkv, dscale, dbias_tab = ops.window_attn_bwd(qkv, inv_norm, scale_c, bias_c, o, d_o, lse, B, H, W, C, heads, Wh, Ww,
-                                                       s0, s1, mode)
-        dbias_qkv = ops.colsum(dqkv)
+                                                       s0, s1, mode, dscale=acc["dscale"])
+        dbias_qkv = ops.colsum(dqkv, out=acc["b_qkv"])
         dx_in = ops.gemm(mode, dqkv, 0, wq, 1, EPI_ADD_F32, aux=dx_mid)                          # fp32 (T, C)
-        dw_qkv = wgrad(dqkv, xb, 3 * C, C)
+        dw_qkv = wgrad(dqkv, xb, 3 * C, C, "w_qkv")
         return (dx_in.view(B, H, W, C), None, dscale, dbias_tab, dw_qkv, dbias_qkv, dw_proj, dbias_proj, dg1, db1, dw_fc1,
                 dbias_fc1, dw_fc2, dbias_fc2, dg2, db2, None, None, None, None)
 

@@ -176,10 +176,13 @@ def ln_residual_fwd(z, x_in, gamma, beta, sample_scale, pos, rows_per_sample: in
     return x_out, xb, stats
 
 
-def ln_residual_bwd(dx, z, stats, gamma, sample_scale, rows_per_sample: int, mode: ComputeMode, want_dbias_prev=True):
+def ln_residual_bwd(dx, z, stats, gamma, sample_scale, rows_per_sample: int, mode: ComputeMode, want_dbias_prev=True,
+                    acc: Optional[torch.Tensor] = None):
+    """`acc`: optional pre-zeroed (3, C) fp32 accumulator (dgamma, dbeta, dbias_prev)."""
     rows, C = z.shape
     dz = torch.empty((rows, C), dtype=mode.act_dtype, device=z.device)
-    acc = torch.zeros((3, C), dtype=torch.float32, device=z.device)
+    if acc is None:
+        acc = torch.zeros((3, C), dtype=torch.float32, device=z.device)
     _lib.call("swinb200_ln_residual_bwd", _chk(dx, "dx", torch.float32), _chk(z, "z", mode.act_dtype), mode.act_code,
               _chk(stats, "stats", torch.float32), _chk(gamma, "gamma", torch.float32),
               _chk(sample_scale, "sample_scale", torch.float32, True), dz.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(),
@@ -200,9 +203,11 @@ def pos_embed_grad(dx: torch.Tensor, B: int, rows_per_sample: int, C: int) -> to
     return dpos
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`out`: optional pre-zeroed (cols,) fp32 accumulator."""
     rows, cols = x.shape
-    out = torch.zeros((cols,), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.zeros((cols,), dtype=torch.float32, device=x.device)
     _lib.call("swinb200_colsum", _chk(x, "x"), _code(x.dtype), out.data_ptr(), rows, cols, cols, _stream())
     return out
 
@@ -245,12 +250,13 @@ def window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, Wh, Ww, s0, s1, mode: C
 
 
 def window_attn_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, B, H, W, C, heads, Wh, Ww, s0, s1, mode: ComputeMode,
-                    backend=None):
+                    backend=None, dscale: Optional[torch.Tensor] = None):
     L = Wh * Ww
     if backend is None:
         backend = attn_backend_for(mode, C, heads, Wh, Ww)
     dqkv = torch.empty_like(qkv)
-    dscale = torch.zeros((heads,), dtype=torch.float32, device=qkv.device)
+    if dscale is None:
+        dscale = torch.zeros((heads,), dtype=torch.float32, device=qkv.device)
     dbias = torch.zeros((heads, L, L), dtype=torch.float32, device=qkv.device) if bias is not None else None
     _lib.call("swinb200_window_attn_bwd", backend, _chk(qkv, "qkv"), _code(qkv.dtype),
               _chk(inv_norm, "inv_norm", torch.float32), _chk(scale, "scale", torch.float32),
