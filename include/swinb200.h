@@ -54,13 +54,15 @@ int swinb200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* strea
  *            (swinv2_global.py:537,544; weight (E, C, P, P) flattened).
  *   order 1: column k = (p*P + q)*C + c -- the inverse of forward_head's unpatchify
  *            (swinv2_global.py:789-791); used on dL/dpred in backward.
- * swinb200_unpatchify: y (T, P*P*Co) act, columns (p, q, c) -> out (B, Co, Hi, Wi) fp32,
- *   out = unpatchify(y) + skip[:, :Co] (skip nullable; skip has skip_chans channels)
- *   (swinv2_global.py:789-791, 795-802). */
+ * swinb200_unpatchify: y (T, P*P*Co) act -> out (B, Co, Hi, Wi) fp32,
+ *   out = unpatchify(y) + skip[:, :Co] (skip nullable; skip has skip_chans channels).
+ *   order 1: columns (p, q, c) -- forward_head's einsum "nhwpqc->nchpwq" (swinv2_global.py:789-791, 795-802);
+ *   order 0: columns (c, p, q) -- adjoint of the PatchEmbed im2col (dL/d image for MultiStepWrapper rollouts,
+ *            networks/helpers.py:26-41). */
 int swinb200_patchify(const float* img, void* out, int act_dtype, int B, int C, int Hi, int Wi, int P,
                       int order, void* stream);
 int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out,
-                        int B, int Co, int Hi, int Wi, int P, void* stream);
+                        int B, int Co, int Hi, int Wi, int P, int order, void* stream);
 
 /* ---- GEMM ---------------------------------------------------------------------------------------
  * D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ).

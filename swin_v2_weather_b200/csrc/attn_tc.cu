@@ -695,7 +695,9 @@ struct BwdSmem {
   static constexpr int kOffDv = kOffLse + kMaxLP * 4;
   static constexpr int kOffRed = kOffDv + kMaxLP * 4;
   static constexpr int kOffBar = kOffRed + 64;
-  static constexpr int kBytes = kOffBar + 64;
+  static constexpr int kOffTok2 = kOffBar + 64;                  // persistent kernel: next item's token table
+  static constexpr int kOffDsc = kOffTok2 + kMaxLP * 4;          // persistent kernel: per-head d(scale) partials
+  static constexpr int kBytes = kOffDsc + 128;
 };
 
 template <int D>
@@ -1106,6 +1108,454 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
 }
 
+template <int D>
+__global__ void __launch_bounds__(256, 1)
+attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ inv_norm, const float* __restrict__ scale_p,
+                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dscale,
+                   float* __restrict__ dbias, const AttnGeom g) {
+  using SM = BwdSmem<D>;
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sQ = smem + SM::kOffQ;
+  unsigned char* sK = smem + SM::kOffK;
+  unsigned char* sV = smem + SM::kOffV;
+  unsigned char* sG = smem + SM::kOffG;
+  unsigned char* sP = smem + SM::kOffP;
+  unsigned char* sDS = smem + SM::kOffDS;
+  int* tok = reinterpret_cast<int*>(smem + SM::kOffTok);   // token table of the current item (double-buffered)
+  float* lse2 = reinterpret_cast<float*>(smem + SM::kOffLse);   // log2-domain LSE per query (+inf for pad queries)
+  float* Dv = reinterpret_cast<float*>(smem + SM::kOffDv);      // rowsum(dO o O) per query
+  float* red = reinterpret_cast<float*>(smem + SM::kOffRed);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long ph_acc[12];
+  for (int i = 0; i < 12; ++i) ph_acc[i] = 0;
+  long long ph_t = clock64();
+#define SWB_ACC(i) do { if (tid == 0) { const long long now_ = clock64(); ph_acc[i] += now_ - ph_t; ph_t = now_; } } while (0)
+  const int L = g.L, LP = g.LP, C = g.C, C3 = 3 * g.C;
+  const int ntiles = (L > 128) ? 2 : 1;
+  const bool shifted = (g.s0 > 0) || (g.s1 > 0);
+  const int nitems = g.B * g.nW * g.heads;
+  int* tokbuf[2] = {tok, reinterpret_cast<int*>(smem + SM::kOffTok2)};
+  float* dsc_heads = reinterpret_cast<float*>(smem + SM::kOffDsc);     // per-head d(scale) partial sums of this CTA
+
+  // ---- one-time set-up: barrier, tensor memory, zero pad rows (gathers only ever write rows < L) -------------------
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < (LP - L) * SM::kChunks * 4; i += 256) {
+    const int op = i / ((LP - L) * SM::kChunks);
+    const int rem = i - op * (LP - L) * SM::kChunks;
+    const int c = rem / (LP - L), r = L + rem % (LP - L);
+    *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid < 32) dsc_heads[tid] = 0.f;
+  // operands op_lo..op_hi-1 (0 Q^, 1 K^, 2 V, 3 dO) of the (window, head) whose token table is `tk`
+  auto gather = [&](int op_lo, int op_hi, const int* tk, int hd) {
+    const int per_op = L * SM::kChunks;
+    for (int i = tid; i < (op_hi - op_lo) * per_op; i += 256) {
+      const int op = op_lo + i / per_op;
+      const int rem = i % per_op;
+      const int n = rem / SM::kChunks, c = rem - n * SM::kChunks;
+      const __nv_bfloat16* src = (op < 3) ? qkv + (size_t)tk[n] * C3 + op * C + hd * D + c * 8
+                                          : d_o + (size_t)tk[n] * C + hd * D + c * 8;
+      cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
+    }
+  };
+  auto fill_tok = [&](int item, int* tk) {
+    const int hd = item % g.heads;
+    const int ww = (item / g.heads) % g.nW;
+    const int bb = item / (g.heads * g.nW);
+    for (int n = tid; n < LP; n += 256) {
+      int rr;
+      tk[n] = (n < L) ? win_token(g, bb, ww, n, rr) : -1;
+    }
+    return hd;
+  };
+  if ((int)blockIdx.x < nitems) fill_tok(blockIdx.x, tokbuf[0]);
+  __syncthreads();
+  if ((int)blockIdx.x < nitems) gather(0, 4, tokbuf[0], (int)blockIdx.x % g.heads);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), g0 = smem_u32(sG), p0 = smem_u32(sP), ds0 = smem_u32(sDS);
+  const uint32_t idesc_s = umma_idesc_bf16(128, LP, false, false);      // [128 x LP] = A(k-major) * B(k-major)^T
+  const uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);        // [128 x D]  = A(k-major) * B(n-major)
+  uint32_t parity = 0;
+  SWB_ACC(1);
+
+  int it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+  tok = tokbuf[it & 1];
+  int* tok_next = tokbuf[(it & 1) ^ 1];
+  const int head = item % g.heads;
+  const int w = (item / g.heads) % g.nW;
+  const int b = item / (g.heads * g.nW);
+  const int item_next = item + gridDim.x;
+  const bool has_next = item_next < nitems;
+  const int head_next = has_next ? fill_tok(item_next, tok_next) : 0;    // visible after the next barrier
+  int label_split = LP;
+  if (shifted) {
+    const int wh = w / g.nWw;
+    if (g.s0 > 0) {
+      const int first_row = g.H - g.s0 - wh * g.Wh;
+      label_split = first_row <= 0 ? 0 : (first_row >= g.Wh ? LP : first_row * g.Ww);
+    } else {
+      label_split = 0;
+    }
+  }
+  for (int n = tid; n < LP; n += 256)
+    lse2[n] = (n < L) ? lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] * kLog2e : INFINITY;
+  const float scale = scale_p[head];
+  const float scale_l2 = scale * kLog2e;
+  cp_async_wait_all();            // this item's operands (gathered during the previous item, or just above)
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  SWB_ACC(2);
+  tc_fence_after();
+  const bool plain = (bias == nullptr) && !(label_split > 0 && label_split < L);
+
+  const int r = (warp & 3) * 32 + lane;                 // row inside the current 128-row tile == TMEM lane
+  const int half = warp >> 2;                           // which part of the LP columns this thread handles
+  const int c_split = ((LP + 31) / 32) * 16;            // both parts are multiples of 16 columns (176 -> 96 + 80)
+  const int c_begin = half ? c_split : 0, c_end = half ? LP : c_split;
+  const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  float dsc_acc = 0.f;
+
+  // ================================ sweep A: query-major -> dq ================================
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // S = Q^_t K^T
+        umma_bf16_ss(tmem_base, umma_desc_nosw(q0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
+                     umma_desc_nosw(k0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // dP = dO_t V^T
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(g0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
+                     umma_desc_nosw(v0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+      umma_commit(bar);
+    }
+    if (t == 0) {
+      // D_n = <dO_n, O_n> for every query of the window, while the first MMAs run
+      for (int n = tid; n < LP; n += 256) {
+        float acc = 0.f;
+        if (n < L) {
+          const __nv_bfloat16* go = d_o + (size_t)tok[n] * C + head * D;
+          const __nv_bfloat16* oo = o + (size_t)tok[n] * C + head * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) {
+            float a8[8], b8[8];
+            ld8(go + c, a8);
+            ld8(oo + c, b8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(a8[e], b8[e], acc);
+          }
+        }
+        Dv[n] = acc;
+      }
+      __syncthreads();
+    }
+    mbar_wait(bar, parity, 600 + t);
+    SWB_ACC(3);
+    parity ^= 1;
+    tc_fence_after();
+    {
+      const int n = t * 128 + r;                        // query slot of this thread
+      const bool row_ok = n < L;
+      const float my_lse = row_ok ? lse2[n] : INFINITY;  // pad rows: p = 2^(-inf) = 0
+      const float my_D = row_ok ? Dv[n] : 0.f;
+      unsigned char* myDS = sDS + r * 16;
+      float dsc_tile = 0.f;
+      if (plain) {
+        // dS = P o (dP - D), P = 2^(scale*cos - lse); loads of the next 16 columns overlap this chunk's arithmetic
+        uint32_t sa[16], pa[16], sb[16], pb[16];
+        tmem_ld_32x16(t_lane + c_begin, sa);
+        tmem_ld_32x16(t_lane + kMaxLP + c_begin, pa);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 16 < c_end;
+          if (has_b) {
+            tmem_ld_32x16(t_lane + c0 + 16, sb);
+            tmem_ld_32x16(t_lane + kMaxLP + c0 + 16, pb);
+          }
+          {
+            float ds[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float cosv = as_f(sa[j]);
+              const float p = ex2_approx(fmaf(cosv, scale_l2, -my_lse));
+              ds[j] = p * (as_f(pa[j]) - my_D);
+              if (c0 + 16 > L && c0 + j >= L) ds[j] = 0.f;
+              dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            }
+            *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+            *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+          }
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < c_end) {
+              tmem_ld_32x16(t_lane + c0 + 32, sa);
+              tmem_ld_32x16(t_lane + kMaxLP + c0 + 32, pa);
+            }
+            const int c1 = c0 + 16;
+            float ds[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float cosv = as_f(sb[j]);
+              const float p = ex2_approx(fmaf(cosv, scale_l2, -my_lse));
+              ds[j] = p * (as_f(pb[j]) - my_D);
+              if (c1 + 16 > L && c1 + j >= L) ds[j] = 0.f;
+              dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            }
+            *reinterpret_cast<uint4*>(myDS + (c1 / 8) * SM::kPCS) = pack8(ds, 0);
+            *reinterpret_cast<uint4*>(myDS + (c1 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+          }
+        }
+      } else {
+        const int my_label = (n >= label_split) ? 1 : 0;
+        const float* brow = (bias != nullptr && row_ok) ? bias + ((size_t)head * L + n) * L : nullptr;
+        float* dbrow = (dbias != nullptr && row_ok) ? dbias + ((size_t)head * L + n) * L : nullptr;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+          uint32_t sv[16], pv[16];
+          tmem_ld_32x16(t_lane + c0, sv);
+          tmem_ld_32x16(t_lane + kMaxLP + c0, pv);
+          tmem_ld_wait();
+          float ds[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int key = c0 + j;
+            const float cosv = as_f(sv[j]);
+            float s = cosv * scale_l2;
+            if (brow != nullptr && key < L) s += brow[key] * kLog2e;
+            if (((key >= label_split) ? 1 : 0) != my_label) s += -100.0f * kLog2e;
+            const float p = (key < L && row_ok) ? ex2_approx(s - my_lse) : 0.f;
+            // pad rows / pad keys read whatever follows the real rows in shared memory: keep them exactly zero
+            ds[j] = (key < L && row_ok) ? p * (as_f(pv[j]) - my_D) : 0.f;
+            if (key < L && row_ok) dsc_tile = fmaf(ds[j], cosv, dsc_tile);
+            if (dbrow != nullptr && key < L) atomicAdd(dbrow + key, ds[j]);
+          }
+          *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+          *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+        }
+      }
+      if (row_ok) dsc_acc += dsc_tile;   // pad rows carry garbage cosines (their P is 0, but 0 * NaN would poison the sum)
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    SWB_ACC(4);
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < LP / 16; ++k)     // dQ^_t = dS K^   (K^ read n-major: rows = keys = k-dimension)
+        umma_bf16_ss(tmem_base, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(k0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 610 + t);
+    SWB_ACC(5);
+    parity ^= 1;
+    tc_fence_after();
+    const int rows_here = min(128, L - t * 128);
+    if (half == 0) {
+      // dq = inv_norm * (dq^ - q^ <q^, dq^>),  dq^ = scale * (dS K^);  the dS tile is dead: stage the rows there
+      const int n = t * 128 + r;
+      const bool row_ok = n < L;
+      float dq[D];
+      float dot = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dq[c0 + j] = as_f(v[j]) * scale;
+      }
+      if (row_ok) {
+        float qh[D];
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+          float t8[8];
+          ld8(reinterpret_cast<const __nv_bfloat16*>(sQ + c * SM::kCS + n * 16), t8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            qh[c * 8 + e] = t8[e];
+            dot = fmaf(t8[e], dq[c * 8 + e], dot);
+          }
+        }
+        const float inq = inv_norm[(size_t)tok[n] * 2 * g.heads + head];
+#pragma unroll
+        for (int c = 0; c < D; ++c) dq[c] = inq * (dq[c] - qh[c] * dot);
+        park_row<D>(sDS, r, dq);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // dQ^ has been read (the next S may overwrite it) and the staged rows are complete
+    scatter_rows<D>(sDS, rows_here, tok, t * 128, dqkv, C3, head * D, tid, 256);
+    __syncthreads();      // staging drained before the next tile's dS lands in the same buffer
+    SWB_ACC(6);
+  }
+
+  // ================================ sweep B: key-major -> dk, dv ================================
+  for (int u = 0; u < ntiles; ++u) {
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // S^T = K^_u Q^T
+        umma_bf16_ss(tmem_base, umma_desc_nosw(k0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
+                     umma_desc_nosw(q0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)      // dP^T = V_u dO^T
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(v0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
+                     umma_desc_nosw(g0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 620 + u);
+    SWB_ACC(7);
+    parity ^= 1;
+    tc_fence_after();
+    // K^ and V have served their last MMA of this item: start gathering the next item's K^ / V into them
+    if (u == ntiles - 1 && has_next) gather(1, 3, tok_next, head_next);
+    {
+      const int jk = u * 128 + r;                       // key slot of this thread
+      const bool key_ok = jk < L;
+      const int key_label = (jk >= label_split) ? 1 : 0;
+      unsigned char* myP = sP + r * 16;
+      unsigned char* myDS = sDS + r * 16;
+      // columns = queries; lse2[q] = +inf for pad queries -> P = 0 there.  Pad key rows only feed discarded output rows,
+      // but they are zeroed so that no NaN ever enters the tensor pipe.
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t sv[16], pv[16];
+        tmem_ld_32x16(t_lane + c0, sv);
+        tmem_ld_32x16(t_lane + kMaxLP + c0, pv);
+        float ls[16], dd[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(&ls[j]) = *reinterpret_cast<const float4*>(&lse2[c0 + j]);
+          *reinterpret_cast<float4*>(&dd[j]) = *reinterpret_cast<const float4*>(&Dv[c0 + j]);
+        }
+        tmem_ld_wait();
+        float pp[16], ds[16];
+        if (plain) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p = ex2_approx(fmaf(as_f(sv[j]), scale_l2, -ls[j]));
+            pp[j] = key_ok ? p : 0.f;
+            ds[j] = key_ok ? p * (as_f(pv[j]) - dd[j]) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int qi = c0 + j;
+            float s = as_f(sv[j]) * scale_l2;
+            if (bias != nullptr && key_ok && qi < L) s += bias[((size_t)head * L + qi) * L + jk] * kLog2e;
+            if (((qi >= label_split) ? 1 : 0) != key_label) s += -100.0f * kLog2e;
+            const float p = key_ok ? ex2_approx(s - ls[j]) : 0.f;
+            pp[j] = p;
+            ds[j] = (key_ok && qi < L) ? p * (as_f(pv[j]) - dd[j]) : 0.f;
+          }
+        }
+        *reinterpret_cast<uint4*>(myP + (c0 / 8) * SM::kPCS) = pack8(pp, 0);
+        *reinterpret_cast<uint4*>(myP + (c0 / 8 + 1) * SM::kPCS) = pack8(pp, 8);
+        *reinterpret_cast<uint4*>(myDS + (c0 / 8) * SM::kPCS) = pack8(ds, 0);
+        *reinterpret_cast<uint4*>(myDS + (c0 / 8 + 1) * SM::kPCS) = pack8(ds, 8);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    SWB_ACC(8);
+    if (tid == 0) {
+      tc_fence_after();
+      for (int k = 0; k < LP / 16; ++k)     // dV_u = P^T dO   (dO read n-major: rows = queries = k-dimension)
+        umma_bf16_ss(tmem_base, umma_desc_nosw(p0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(g0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      for (int k = 0; k < LP / 16; ++k)     // dK^_u = dS^T Q^
+        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
+                     umma_desc_nosw(q0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity, 630 + u);
+    SWB_ACC(9);
+    parity ^= 1;
+    tc_fence_after();
+    // ... and Q^ / dO after the last dV / dK^ MMAs
+    if (u == ntiles - 1 && has_next) {
+      gather(0, 1, tok_next, head_next);
+      gather(3, 4, tok_next, head_next);
+    }
+    const int rows_here = min(128, L - u * 128);
+    {
+      // warps 0-3: dv rows (staged in the P tile); warps 4-7: dk rows (staged in the dS tile)
+      const int jk = u * 128 + r;
+      const bool key_ok = jk < L;
+      float acc[D];
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + half * kMaxLP + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = as_f(v[j]);
+      }
+      if (key_ok) {
+        if (half == 0) {
+          park_row<D>(sP, r, acc);
+        } else {                                         // dk = inv_norm * (dk^ - k^ <k^, dk^>), dk^ = scale * (dS^T Q^)
+          float dot = 0.f;
+          float kh[D];
+#pragma unroll
+          for (int c = 0; c < D / 8; ++c) {
+            float t8[8];
+            ld8(qkv + (size_t)tok[jk] * C3 + C + head * D + c * 8, t8);   // L2-resident; sK may already hold the next item
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              kh[c * 8 + e] = t8[e];
+              acc[c * 8 + e] *= scale;
+              dot = fmaf(t8[e], acc[c * 8 + e], dot);
+            }
+          }
+          const float ink = inv_norm[(size_t)tok[jk] * 2 * g.heads + g.heads + head];
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc[c] = ink * (acc[c] - kh[c] * dot);
+          park_row<D>(sDS, r, acc);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // 128 threads drain each staging tile with whole-row stores
+    if (half == 0) scatter_rows<D>(sP, rows_here, tok, u * 128, dqkv, C3, 2 * C + head * D, tid, 128);
+    else scatter_rows<D>(sDS, rows_here, tok, u * 128, dqkv, C3, C + head * D, tid - 128, 128);
+    __syncthreads();
+    SWB_ACC(10);
+  }
+
+  // ---- d(scale) = sum dS o cos: per-warp partial -> per-head slot of this CTA ------------------------------------------
+  dsc_acc = warp_sum(dsc_acc);
+  if (lane == 0) atomicAdd(&dsc_heads[head], dsc_acc);
+  }   // item loop
+  __syncthreads();
+  if (tid < g.heads) {
+    const float v = dsc_heads[tid];
+    if (v != 0.f) atomicAdd(dscale + tid, v);
+  }
+  if (g_phase_buf != nullptr && tid == 0 && blockIdx.x < 4096)
+    for (int i = 0; i < 12; ++i) g_phase_buf[blockIdx.x * 16 + i] = ph_acc[i];
+#undef SWB_ACC
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale, const float* bias, const void* o,
                      const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W, int C,
                      int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
@@ -1117,9 +1567,26 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
     SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
     configured = true;
   }
-  attn_tc_bwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>(
-      (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
-      (__nv_bfloat16*)dqkv, dscale, dbias, g);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("SWINB200_ATTN_BWD");
+    variant = e ? atoi(e) : 1;   // 2 = persistent kernel with in-place prefetch (experimental, not faster yet)
+  }
+  if (variant == 1) {
+    attn_tc_bwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>(
+        (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
+        (__nv_bfloat16*)dqkv, dscale, dbias, g);
+  } else {
+    static bool configured2 = false;
+    if (!configured2) {
+      SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd2_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+      configured2 = true;
+    }
+    const int grid = min(B * g.nW * heads, sm_count());
+    attn_tc_bwd2_kernel<96><<<grid, 256, SM::kBytes, stream>>>(
+        (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
+        (__nv_bfloat16*)dqkv, dscale, dbias, g);
+  }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }

@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
 }
 
-// y (T, P*P*Co) columns (p, q, c) -> out (B, Co, Hi, Wi) (+ skip[:, :Co])
-template <typename T>
+// y (T, P*P*Co) -> out (B, Co, Hi, Wi) (+ skip[:, :Co]); ORDER 1: columns (p, q, c) (output head), ORDER 0: (c, p, q)
+// (gradient of the PatchEmbed im2col, i.e. dL/d image for multi-step rollouts)
+template <typename T, int ORDER>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y, const float* __restrict__ skip,
                                                          int skip_chans, float* __restrict__ out, int B, int Co, int Hi,
                                                          int Wi, int ntok) {
@@ -133,10 +134,15 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y
     const int j = t % W, i = (t / W) % H, b = t / (W * H);
     const T* row = tile + (size_t)tok * pitch;
     float4 v;
-    v.x = Act<T>::ld(row + (p * P + 0) * Co + c);
-    v.y = Act<T>::ld(row + (p * P + 1) * Co + c);
-    v.z = Act<T>::ld(row + (p * P + 2) * Co + c);
-    v.w = Act<T>::ld(row + (p * P + 3) * Co + c);
+    if (ORDER == 1) {
+      v.x = Act<T>::ld(row + (p * P + 0) * Co + c);
+      v.y = Act<T>::ld(row + (p * P + 1) * Co + c);
+      v.z = Act<T>::ld(row + (p * P + 2) * Co + c);
+      v.w = Act<T>::ld(row + (p * P + 3) * Co + c);
+    } else {
+      const T* s4 = row + (c * P + p) * P;
+      v.x = Act<T>::ld(s4 + 0); v.y = Act<T>::ld(s4 + 1); v.z = Act<T>::ld(s4 + 2); v.w = Act<T>::ld(s4 + 3);
+    }
     const size_t pix = (size_t)(i * P + p) * Wi + j * P;
     if (skip != nullptr) {
       const float4 s = *reinterpret_cast<const float4*>(skip + ((size_t)b * skip_chans + c) * Hi * Wi + pix);
@@ -665,26 +671,33 @@ extern "C" int swinb200_patchify(const float* img, void* out, int act_dtype, int
 }
 
 template <typename T>
-static int launch_unpatchify(const T* y, const float* skip, int skip_chans, float* out, int B, int Co, int Hi, int Wi,
+static int launch_unpatchify(const T* y, const float* skip, int skip_chans, float* out, int B, int Co, int Hi, int Wi, int order,
                              cudaStream_t s) {
   const int ntok = B * (Hi / 4) * (Wi / 4);
   const int K = Co * 16;
   const size_t smem = (size_t)kPatchTok * (K + 8) * sizeof(T);
-  SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unpatchify_kernel<T><<<(ntok + kPatchTok - 1) / kPatchTok, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+  const int blocks = (ntok + kPatchTok - 1) / kPatchTok;
+  if (order == 1) {
+    SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unpatchify_kernel<T, 1><<<blocks, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+  } else {
+    SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unpatchify_kernel<T, 0><<<blocks, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+  }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }
 
 extern "C" int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out, int B, int Co,
-                                   int Hi, int Wi, int P, void* stream) {
+                                   int Hi, int Wi, int P, int order, void* stream) {
+  SWB_CHECK_ARG(order == 0 || order == 1, "unpatchify: order must be 0 or 1");
   SWB_CHECK_ARG(y && out, "unpatchify: null pointer");
   SWB_CHECK_ARG(P == 4, "unpatchify: only patch_size 4 is supported (got %d)", P);
   SWB_CHECK_ARG(B > 0 && Co > 0 && Hi % 4 == 0 && Wi % 4 == 0, "unpatchify: bad shape");
   SWB_CHECK_ARG(skip == nullptr || skip_chans >= Co, "unpatchify: skip has fewer channels (%d) than the output (%d)", skip_chans, Co);
   SWB_CHECK_ARG((size_t)kPatchTok * (Co * 16 + 8) * 4 <= 220 * 1024, "unpatchify: Co=%d too large", Co);
-  if (act_dtype == SWINB200_BF16) return launch_unpatchify<__nv_bfloat16>((const __nv_bfloat16*)y, skip, skip_chans, out, B, Co, Hi, Wi, (cudaStream_t)stream);
-  if (act_dtype == SWINB200_F32) return launch_unpatchify<float>((const float*)y, skip, skip_chans, out, B, Co, Hi, Wi, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_BF16) return launch_unpatchify<__nv_bfloat16>((const __nv_bfloat16*)y, skip, skip_chans, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32) return launch_unpatchify<float>((const float*)y, skip, skip_chans, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
   SWB_CHECK_ARG(false, "unpatchify: bad act_dtype %d", act_dtype);
 }
 

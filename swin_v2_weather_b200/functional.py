@@ -69,7 +69,7 @@ class PatchEmbedFn(torch.autograd.Function):
         if pos_embed is not None:
             pos_tok = ops.transpose_f32(pos_embed.detach().reshape(E, H * W))          # (H*W, E) token-major
         x, xb, stats = ops.ln_residual_fwd(z0, None, norm_w.detach(), norm_b.detach(), None, pos_tok, H * W, mode)
-        ctx.save_for_backward(patches, z0, stats, norm_w)
+        ctx.save_for_backward(patches, z0, stats, norm_w, proj_w)
         ctx.meta = (B, Cin, Hi, Wi, E, H, W, patch, mode, pos_embed is not None, tuple(proj_w.shape))
         shadow = xb if mode.act_dtype != torch.float32 else x.new_empty(0)   # fp32 mode: the stream is its own shadow
         ctx.mark_non_differentiable(shadow)
@@ -77,17 +77,22 @@ class PatchEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx, _dxb):
-        patches, z0, stats, norm_w = ctx.saved_tensors
+        patches, z0, stats, norm_w, proj_w = ctx.saved_tensors
         B, Cin, Hi, Wi, E, H, W, patch, mode, has_pos, wshape = ctx.meta
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. the input image (multi-step rollout) is not implemented yet")
         dx = dx.contiguous().view(B * H * W, E)
         dpos = ops.pos_embed_grad(dx, B, H * W, E).view(1, E, H, W) if has_pos else None
         dz0, dgamma, dbeta, dbias = ops.ln_residual_bwd(dx, z0, stats, norm_w.detach(), None, H * W, mode)
         K = patches.shape[1]
         dw = torch.zeros((E, K), dtype=torch.float32, device=dx.device)
         ops.gemm(mode, dz0, 1, patches, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(E, K, dz0.shape[0]))
-        return None, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None
+        dimg = None
+        if ctx.needs_input_grad[0]:
+            # multi-step rollouts (networks/helpers.py:26-41) back-propagate into the previous step's prediction:
+            # d patches = dz0 @ W (dgrad GEMM, weight read n-major), scattered back by the im2col adjoint
+            w2 = SHADOWS.get(proj_w, mode).reshape(E, -1)
+            dpatch = ops.gemm(mode, dz0, 0, w2, 1, EPI_BIAS)                          # (T, Cin*P*P), columns (c, p, q)
+            dimg = ops.unpatchify(dpatch, None, B, Cin, Hi, Wi, patch, order=0)
+        return dimg, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None
 
 
 # ---- one SwinV2 block ------------------------------------------------------------------------------------

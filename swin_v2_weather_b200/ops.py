@@ -90,11 +90,12 @@ def patchify(img: torch.Tensor, patch: int, order: int, mode: ComputeMode) -> to
     return out
 
 
-def unpatchify(y: torch.Tensor, skip: Optional[torch.Tensor], B: int, Co: int, Hi: int, Wi: int, patch: int) -> torch.Tensor:
+def unpatchify(y: torch.Tensor, skip: Optional[torch.Tensor], B: int, Co: int, Hi: int, Wi: int, patch: int,
+               order: int = 1) -> torch.Tensor:
     out = torch.empty((B, Co, Hi, Wi), dtype=torch.float32, device=y.device)
     skip_ch = 0 if skip is None else skip.shape[1]
     _lib.call("swinb200_unpatchify", _chk(y, "y"), _code(y.dtype), _chk(skip, "skip", torch.float32, True), skip_ch, out.data_ptr(),
-              B, Co, Hi, Wi, patch, _stream())
+              B, Co, Hi, Wi, patch, order, _stream())
     return out
 
 

@@ -70,6 +70,16 @@ def test_unpatchify(dtype, with_skip):
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_unpatchify_is_adjoint_of_patchify(dtype):
+    """order 0 unpatchify inverts order 0 patchify (used for dL/d image in multi-step rollouts)."""
+    B, C, Hi, Wi, P = 2, 7, 72, 144, 4
+    x = gen(B, C, Hi, Wi, seed=1).to(dtype).float()
+    cols = ops.patchify(x, P, 0, mode_for(dtype))
+    back = ops.unpatchify(cols, None, B, C, Hi, Wi, P, order=0)
+    assert torch.equal(back, x)
+
+
 def test_transpose_and_pos_grad():
     src = gen(650, 200, seed=4)
     assert torch.equal(ops.transpose_f32(src), src.t().contiguous())

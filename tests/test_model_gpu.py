@@ -159,3 +159,40 @@ def test_attn_mask_property_bit_exact():
         assert (want is None) == (got is None)
         if want is not None:
             assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_multistep_rollout_gradients(mode):
+    """MultiStepWrapper (networks/helpers.py:18-41): the second step consumes the first step's prediction, so gradients
+    flow through the skip connection and the PatchEmbed im2col back into the first step."""
+    from types import SimpleNamespace
+    from swin_v2_weather_b200.networks.helpers import get_model
+    cfg = O.SwinConfig(img_size=(72, 144), depth=2, num_heads=2, in_chans=6, out_chans=5, embed_dim=192, window_ratio=8,
+                       rel_pos=False, residual=True)
+    params = SimpleNamespace(nettype='swin', n_future=1, add_orography=True, add_landmask=False, img_size=[72, 144], patch_size=4,
+                             depth=2, num_heads=2, n_in_channels=6, n_out_channels=5, embed_dim=192, window_ratio=8,
+                             drop_path_rate=0.0, full_pos_embed=True, rel_pos=False, mlp_ratio=4, activation_ckpt=False,
+                             residual=True, compute_mode=mode)
+    sd = O.init_state_dict(cfg, seed=3)
+    wrapper = get_model(params)
+    wrapper.model.load_state_dict(sd)
+    wrapper = wrapper.cuda().eval()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 6, 72, 144, generator=g)
+    tar = torch.randn(2, 10, 72, 144, generator=g)
+    chw = torch.ones(10) / 10
+    # oracle rollout
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    p1 = O.model_forward(x, leaves, cfg)
+    p2 = O.model_forward(torch.cat([p1, x[:, -1:]], dim=1), leaves, cfg)
+    loss_ref = O.geometric_l2(torch.cat([p1, p2], dim=1), tar, chw, True)
+    grads_ref = dict(zip(leaves.keys(), torch.autograd.grad(loss_ref, list(leaves.values()))))
+    # ours
+    pred = wrapper(x.cuda())
+    qw = O.quadrature_row_weights(72, 144).cuda()
+    loss = LatWeightedL2Fn.apply(pred, tar.cuda(), qw, chw.cuda(), True, True)
+    loss.backward()
+    grads = {k: p.grad.detach().cpu() for k, p in wrapper.model.named_parameters()}
+    tol = 1e-5 if mode == "fp32" else 1e-2
+    check(pred.detach().cpu(), float(loss), grads, torch.cat([p1, p2], dim=1).detach(), loss_ref.detach(), grads_ref, tol,
+          5e-5 if mode == "fp32" else 5e-2)
