@@ -1,11 +1,15 @@
 // tcgen05 GEMM for sm_100a:  D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ),  bf16 operands, fp32 accumulation in TMEM.
 //
 // Persistent, warp-specialised, one CTA per SM (576 threads):
-//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1      MMA issuer     (one thread: tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM)
-//   warps 2..17 epilogue       (four groups of 4 warps; group g owns every fourth 64-byte column chunk of the tile:
+//   warps 0..15 epilogue       (four groups of 4 warps; group g owns every fourth 64-byte column chunk of the tile:
 //                               tcgen05.ld -> fused epilogue in registers -> swizzled smem staging -> TMA store /
 //                               TMA reduce-add, so global writes are whole 64-byte row pieces issued by the copy engine)
+//   warp 16     TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 17     MMA issuer     (tcgen05.mma 128 x BN x 16 by one elected lane, accumulators double-buffered in TMEM)
+// The two single-lane roles sit in the HIGHEST warp ids of their scheduler partitions: the issue arbiter favours the
+// highest warp id, and the MMA loop is latency-critical (its ~40 instructions per k-block must not queue behind the
+// epilogue warps' arithmetic, which is what capped the GELU GEMMs at 54 % tensor-pipe activity).  Both loops run
+// warp-convergent with the issuing lane elected per instruction, so descriptors live in uniform registers.
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
 // token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
@@ -22,7 +26,10 @@ constexpr int GBM = 128;  // UMMA M (cta_group::1)
 constexpr int GBK = 64;   // k per pipeline stage (one 128-byte swizzle row of bf16)
 constexpr int kEpiGroups = 4;             // epilogue groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int kGemmThreads = 64 + kEpiGroups * 128;
-constexpr int kStagingBytes = 128 * 64;    // one [128 rows x 64 B] output chunk per epilogue group
+constexpr int kProducerWarp = kEpiGroups * 4, kMmaWarp = kEpiGroups * 4 + 1;
+constexpr int kStagingBytes = 32 * 64;     // one [32 rows x 64 B] output piece per epilogue WARP
+constexpr int kStagingBufs = 2;            // staging buffers per warp: a store only waits for the one before the previous one
+constexpr int kBiasBytes = 2048;           // per-group bias slices (<= 64 floats per group), double-buffered by tile parity
 
 struct GemmTcParams {
   int M, N, K;
@@ -44,11 +51,13 @@ struct GemmCfg {
   static constexpr int kStageA = GBM * GBK * 2;
   static constexpr int kStageB = (PAIR ? BN / 2 : BN) * GBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = PAIR ? 6 : ((BN >= 192) ? 4 : 6);
+  static constexpr int kStages = PAIR ? 5 : ((BN >= 192) ? 3 : 5);   // 5 x 32 KB stages + 64 KB of staging fill the SM
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kOffStaging = kStages * kStage;
-  static constexpr int kOffBars = kOffStaging + kEpiGroups * kStagingBytes;
-  static constexpr int kSmem = kOffBars + 256 + 1024 /* alignment slack */;
+  static constexpr int kOffBars = kOffStaging + kEpiGroups * 4 * kStagingBufs * kStagingBytes;
+  static constexpr int kOffBias = kOffBars + 256;
+  static constexpr int kSmem = kOffBias + kBiasBytes;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
 // GELU in the epilogue has an instruction budget: a 128x256 tile with K = 768 keeps the tensor pipe busy for ~6.1k
@@ -70,6 +79,43 @@ __device__ __forceinline__ float normal_cdf_fast(float x) {
   return fmaf(xc, p, 0.5f);
 }
 __device__ __forceinline__ float gelu_fast(float x) { return x * normal_cdf_fast(x); }
+
+// Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction, operands in 64-bit register
+// pairs).  The epilogues are issue-slot bound, so evaluating the polynomial two columns at a time halves their cost.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 splat2(float c) { return pack2(c, c); }
+// normal_cdf_fast on two values (same polynomial, same rounding: fma.rn per lane)
+__device__ __forceinline__ f32x2 normal_cdf_fast2(float x0, float x1) {
+  const f32x2 xc = pack2(fminf(fmaxf(x0, -4.0f), 4.0f), fminf(fmaxf(x1, -4.0f), 4.0f));
+  const f32x2 u = mul2(xc, xc);
+  f32x2 q = splat2(-1.5809101805430714e-09f);
+  q = fma2(q, u, splat2(1.21718073842203e-07f));
+  q = fma2(q, u, splat2(-4.101022113900399e-06f));
+  q = fma2(q, u, splat2(8.066916052484885e-05f));
+  q = fma2(q, u, splat2(-0.001048215082846582f));
+  q = fma2(q, u, splat2(0.009664907120168209f));
+  q = fma2(q, u, splat2(-0.0661754235625267f));
+  q = fma2(q, u, splat2(0.3988475203514099f));
+  return fma2(xc, q, splat2(0.5f));
+}
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
+  unpack2(mul2(pack2(x0, x1), normal_cdf_fast2(x0, x1)), g0, g1);
+}
+// v{0,1} *= d/dx[x Phi(x)] at h{0,1}
+__device__ __forceinline__ void gelu_grad_mul2(float h0, float h1, float& v0, float& v1) {
+  const f32x2 x = pack2(h0, h1);
+  float a0, a1, e0, e1;
+  unpack2(mul2(mul2(x, x), splat2(-0.72134752044448170368f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 d = fma2(mul2(x, splat2(0.39894228040143267794f)), pack2(e0, e1), normal_cdf_fast2(h0, h1));
+  unpack2(mul2(pack2(v0, v1), d), v0, v1);
+}
 // d/dx [x Phi(x)] = Phi(x) + x phi(x),  phi(x) = exp(-x^2/2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float e;
@@ -98,6 +144,12 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- cta_group::2 (CTA pair) forms.  Shared-window addresses of the two CTAs of a pair differ in bit 24; clearing it
 // addresses the leader (even) CTA's copy of the same variable (CUTLASS: Sm100MmaPeerBitMask).
@@ -162,8 +214,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kChunkCols = kF32Out ? 16 : 32;          // 64 bytes of output per row per chunk
   constexpr int kNumChunks = BN / kChunkCols;
   constexpr bool kHasAux = (EPI == SWINB200_EPI_DGELU || EPI == SWINB200_EPI_ADD_F32);
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) unsigned char smem[];   // 128B-swizzled stages need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
@@ -173,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmD);
@@ -188,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
@@ -200,20 +252,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // =============================== TMA producer ===============================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
-        const int ks = tile % p.split_k;
-        const int rest = tile / p.split_k;
-        const int n0 = (rest % p.num_n_tiles) * BN + (int)crank * BNL;            // PAIR: this CTA's half of the B columns
-        const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+  if (warp == kProducerWarp) {
+    // =============================== TMA producer (warp-convergent, one elected lane issues) ====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      const int ks = tile % p.split_k;
+      const int rest = tile / p.split_k;
+      const int n0 = (rest % p.num_n_tiles) * BN + (int)crank * BNL;            // PAIR: this CTA's half of the B columns
+      const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
+      const int kb0 = ks * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+        if (elect_one()) {
           unsigned char* sa = smem + stage * Cfg::kStage;
           unsigned char* sb = sa + Cfg::kStageA;
           // PAIR: every load of both CTAs completes on the leader's barrier, which expects both CTAs' bytes
@@ -238,17 +290,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < BNL / 64; ++c)  // box {64 n, 64 k}
               load(sb + c * (64 * GBK * 2), &tmB, n0 + c * 64, k0);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+  } else if (warp == kMmaWarp) {
+    if (crank == 0) {
       // =============================== MMA issuer (leader CTA only in PAIR mode) =================================
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * GBM : GBM, BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart, k advances 32 B inside the swizzle row.
       // MN-major: 8-k groups 1024 B apart, 64-wide m/n chunks 64*128 B apart, k advances 16 rows = 2048 B.
+      // Descriptors are built once; stage and k only move the 16-byte-unit start address in the low word.
       constexpr uint32_t kLboMn = 64 * GBK * 2;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? umma_smem_desc_sw128(smem0, kLboMn, 1024) : umma_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? umma_smem_desc_sw128(smem0 + Cfg::kStageA, kLboMn, 1024)
+                                   : umma_smem_desc_sw128(smem0 + Cfg::kStageA, 16, 1024);
+      constexpr uint32_t kAStep = (A_MN ? 2048 : 32) >> 4, kBStep = (B_MN ? 2048 : 32) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -264,33 +323,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t sb = sa + Cfg::kStageA;
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)(stage * (Cfg::kStage >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(stage * (Cfg::kStage >> 4));
 #pragma unroll
-          for (int k = 0; k < GBK / 16; ++k) {
-            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sa + k * 2048, kLboMn, 1024)
-                                        : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, kLboMn, 1024)
-                                        : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (PAIR) umma_bf16_ss_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GBK / 16; ++k) {
+              if (PAIR) umma_bf16_ss_pair(tmem_d, ad + k * kAStep, bd + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16_ss(tmem_d, ad + k * kAStep, bd + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue (of both CTAs)
+            if (kb == kb1 - 1) { if (PAIR) umma_commit_pair(&tfull_bar[buf]); else umma_commit(&tfull_bar[buf]); }
           }
-          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue (of both CTAs)
-        if (PAIR) umma_commit_pair(&tfull_bar[buf]); else umma_commit(&tfull_bar[buf]);
       }
     }
   } else {
     // ================================= epilogue ===================================
-    const int ew = warp - 2;               // 0 .. 4*kEpiGroups-1
+    const int ew = warp;                   // 0 .. 4*kEpiGroups-1
     const int grp = ew >> 2;               // epilogue group: owns chunks grp, grp + kEpiGroups, ...
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;     // row inside the tile
-    const bool issuer = (ew & 3) == 0 && lane == 0;
-    unsigned char* stg0 = smem + Cfg::kOffStaging + grp * kStagingBytes;       // one staging buffer per group
+    const int gt = threadIdx.x & 127;      // thread index inside the group (group g = warps 4g .. 4g+3)
+    unsigned char* stg_base = smem + Cfg::kOffStaging + ew * kStagingBufs * kStagingBytes;
+    uint32_t stg_sel = 0;                  // staging buffer of the next piece
+    // Each warp stages and stores its own 32 rows: no cross-warp barrier sits between tcgen05.ld and the TMA store.
+    constexpr bool kBiasEpi = (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU);
+    constexpr int kChunksPerGroup = (kNumChunks + kEpiGroups - 1) / kEpiGroups;
+    constexpr int kBiasSlots = kChunksPerGroup * kChunkCols;
+    static_assert(!kBiasEpi || kBiasSlots <= 64, "bias slices must fit");
+    float* sbias_grp = reinterpret_cast<float*>(smem + Cfg::kOffBias) + grp * 64;   // + 256 floats for odd tiles
+    const bool has_bias = kBiasEpi && p.bias != nullptr;
+    const int mrow0 = quarter * 32;        // first tile row of this warp
     int local = 0;
     for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++local) {
       const int rest = tile / p.split_k;
@@ -298,8 +365,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
       const int buf = local & 1;
       const uint32_t use = (uint32_t)(local >> 1);
+      // this group's slice of the bias vector goes through shared memory (there is no L1 left beside the 225 KB of
+      // operand stages, so a per-chunk __ldg would expose an L2 round trip): fetched before the accumulator wait
+      float bias_v = 0.f;
+      if (kBiasEpi && has_bias && gt < kBiasSlots) {
+        const int chb = grp + (gt / kChunkCols) * kEpiGroups;
+        const int col = n0 + chb * kChunkCols + (gt % kChunkCols);
+        if (chb < kNumChunks && col < p.N) bias_v = __ldg(p.bias + col);
+      }
       mbar_wait(&tfull_bar[buf], use & 1, 400 + buf);
       tc_fence_after();
+      // double-buffered by tile parity: a warp can only be one barrier ahead of the slowest warp of its group, so the
+      // slice being overwritten (two tiles old) has no readers left
+      float* sbias = sbias_grp + (local & 1) * 256;
+      if (kBiasEpi && has_bias) {
+        if (gt < kBiasSlots) sbias[gt] = bias_v;
+        group_bar(1 + grp);
+      }
       const int m = m0 + r;
       const bool row_ok = m < p.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
@@ -343,20 +425,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          unsigned char* stg = stg0;
-          if (issuer) bulk_wait_read0();
-          group_bar(1 + grp);
+          unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
+          stg_sel ^= 1;
+          if (lane == 0) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+          __syncwarp();
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 pk;
             pk.x = pack_bf16x2(v[q * 32 + c * 8 + 0], v[q * 32 + c * 8 + 1]); pk.y = pack_bf16x2(v[q * 32 + c * 8 + 2], v[q * 32 + c * 8 + 3]);
             pk.z = pack_bf16x2(v[q * 32 + c * 8 + 4], v[q * 32 + c * 8 + 5]); pk.w = pack_bf16x2(v[q * 32 + c * 8 + 6], v[q * 32 + c * 8 + 7]);
-            *reinterpret_cast<uint4*>(staging_chunk(stg, r, c)) = pk;
+            *reinterpret_cast<uint4*>(staging_chunk(stg0, lane, c)) = pk;
           }
           fence_proxy_async_smem();
-          group_bar(1 + grp);
-          if (issuer) {
-            tma_store_2d(&tmD, stg, nh0 + q * 32, m0);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmD, stg0, nh0 + q * 32, m0 + mrow0);
             bulk_commit();
           }
         }
@@ -402,14 +485,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
         }
-        if (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU) {
-          if (p.bias != nullptr) {
+        if (kBiasEpi) {
+          if (has_bias) {
+            const float4* b4p = reinterpret_cast<const float4*>(sbias + ((ch - grp) / kEpiGroups) * kChunkCols);
 #pragma unroll
-            for (int g = 0; g < kChunkCols / 4; ++g)
-              if (nb + g * 4 < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + g * 4));
-                v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-              }
+            for (int g = 0; g < kChunkCols / 4; ++g) {
+              const float4 b4 = b4p[g];
+              unpack2(add2(pack2(v[g * 4 + 0], v[g * 4 + 1]), pack2(b4.x, b4.y)), v[g * 4 + 0], v[g * 4 + 1]);
+              unpack2(add2(pack2(v[g * 4 + 2], v[g * 4 + 3]), pack2(b4.z, b4.w)), v[g * 4 + 2], v[g * 4 + 3]);
+            }
           }
         } else if (EPI == SWINB200_EPI_DGELU) {
 #pragma unroll
@@ -418,7 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             unpack_bf16x2(aux_cur[g].x, h8[0], h8[1]); unpack_bf16x2(aux_cur[g].y, h8[2], h8[3]);
             unpack_bf16x2(aux_cur[g].z, h8[4], h8[5]); unpack_bf16x2(aux_cur[g].w, h8[6], h8[7]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[g * 8 + e] *= gelu_grad_fast(h8[e]);
+            for (int e = 0; e < 8; e += 2) gelu_grad_mul2(h8[e], h8[e + 1], v[g * 8 + e], v[g * 8 + e + 1]);
           }
         } else if (EPI == SWINB200_EPI_ADD_F32) {
 #pragma unroll
@@ -427,43 +511,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[g * 4 + 2] += __uint_as_float(aux_cur[g].z); v[g * 4 + 3] += __uint_as_float(aux_cur[g].w);
           }
         }
-        // ---- stage the chunk and hand it to the copy engine: the group's previous store must have finished *reading*
-        //      the staging buffer; with four groups in flight that wait overlaps the other groups' arithmetic.
-        //      GELU stages the pre-activation first, then the activation.
+        // ---- stage this warp's 32 rows of the chunk and hand them to the copy engine; the warp's previous store must
+        //      have finished *reading* the buffer.  GELU stores the pre-activation first and evaluates the activation
+        //      while the copy engine drains the buffer.
         constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          if (issuer && !(p.debug & 1)) bulk_wait_read0();
-          group_bar(1 + grp);
+          unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
+          stg_sel ^= 1;
+          if (lane == 0 && !(p.debug & 1)) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+          __syncwarp();
+          uint4 pk[4];
           if (kF32Out) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<float4*>(staging_chunk(stg0, r, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+              *reinterpret_cast<float4*>(staging_chunk(stg0, lane, c)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-              pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-              *reinterpret_cast<uint4*>(staging_chunk(stg0, r, c)) = pk;
-              if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) {
-                // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h;
-                // v[] is overwritten with the activation for the second pass
-                float h8[8];
-                unpack_bf16x2(pk.x, h8[0], h8[1]); unpack_bf16x2(pk.y, h8[2], h8[3]);
-                unpack_bf16x2(pk.z, h8[4], h8[5]); unpack_bf16x2(pk.w, h8[6], h8[7]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[c * 8 + e] = gelu_fast(h8[e]);
-              }
+              pk[c].x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk[c].y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+              pk[c].z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk[c].w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+              *reinterpret_cast<uint4*>(staging_chunk(stg0, lane, c)) = pk[c];
             }
           }
           fence_proxy_async_smem();
-          group_bar(1 + grp);
-          if (issuer && !(p.debug & 2)) {
-            if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg0, nb, m0);
-            else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg0, nb, m0);
-            else tma_store_2d(&tmD, stg0, nb, m0);
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 2)) {
+            if (EPI == SWINB200_EPI_F32 && p.atomic_out) tma_reduce_add_2d(&tmD, stg0, nb, m0 + mrow0);
+            else if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) tma_store_2d(&tmD2, stg0, nb, m0 + mrow0);
+            else tma_store_2d(&tmD, stg0, nb, m0 + mrow0);
             bulk_commit();
+          }
+          if (EPI == SWINB200_EPI_BIAS_GELU && pass == 0) {
+            // GELU of the stored (bf16-rounded) pre-activation, so forward and backward see the same h;
+            // v[] is overwritten with the activation for the second pass
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float h8[8];
+              unpack_bf16x2(pk[c].x, h8[0], h8[1]); unpack_bf16x2(pk[c].y, h8[2], h8[3]);
+              unpack_bf16x2(pk[c].z, h8[4], h8[5]); unpack_bf16x2(pk[c].w, h8[6], h8[7]);
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) gelu_fast2(h8[e], h8[e + 1], v[c * 8 + e], v[c * 8 + e + 1]);
+            }
           }
         }
       }
@@ -471,13 +560,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
     }
-    if (issuer) bulk_wait0();   // all global writes of this CTA have completed before it exits
+    if (lane == 0) bulk_wait0();   // all global writes of this warp have completed before the CTA exits
   }
 
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();     // neither CTA leaves (or frees tensor memory) while its peer can still touch it
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -631,12 +720,12 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   if (!b_major) e = make_tmap_2d(&tmB, false, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GBK, (uint32_t)(p.pair ? BN / 2 : BN));
   else e = make_tmap_2d(&tmB, false, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GBK);
   if (e) return e;
-  // output maps: one [128 rows x 64 bytes] box per staged chunk; the copy engine clips rows >= M and columns >= N
-  e = make_tmap_2d(&tmD, f32_out, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, f32_out ? 16 : 32, GBM, true);
+  // output maps: one [32 rows x 64 bytes] box per staged piece; the copy engine clips rows >= M and columns >= N
+  e = make_tmap_2d(&tmD, f32_out, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, f32_out ? 16 : 32, 32, true);
   if (e) return e;
   tmD2 = tmD;
   if (epilogue == SWINB200_EPI_BIAS_GELU) {
-    e = make_tmap_2d(&tmD2, false, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 32, GBM, true);
+    e = make_tmap_2d(&tmD2, false, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 32, 32, true);
     if (e) return e;
   }
 

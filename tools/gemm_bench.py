@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from swin_v2_weather_b200 import ops
 from swin_v2_weather_b200._lib import BACKEND_TCGEN05, EPI_ADD_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_F32
 T, C, HID = 64800, 768, 3072
-def t(f, n=10):
+def t(f, n=20):
     for _ in range(3): f()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     torch.cuda.synchronize(); ev[0].record()
@@ -26,6 +26,10 @@ cases = {
  "fc1 dgrad (ADD_F32)  ": (2*T*HID*C, lambda: ops.gemm(m, dh, 0, w_fc1, 1, EPI_ADD_F32, aux=dxo)),
  "fc1 wgrad (F32 splitK)": (2*T*HID*C, lambda: ops.gemm(m, dh, 1, x, 1, EPI_F32, out=torch.zeros(HID, C, device="cuda"), accumulate=True, split_k=ops.wgrad_split_k(HID, C, T))),
 }
+wq = w_qkv.t().contiguous(); w1 = w_fc1.t().contiguous(); w2 = w_fc2.t().contiguous()
+cases["cuBLAS x@Wqkv (no epilogue)"] = (2*T*3*C*C, lambda: torch.matmul(x, wq))
+cases["cuBLAS x@W1   (no epilogue)"] = (2*T*HID*C, lambda: torch.matmul(x, w1))
+cases["cuBLAS g@W2   (no epilogue)"] = (2*T*HID*C, lambda: torch.matmul(g, w2))
 for k, (fl, f) in cases.items():
     ms = t(f)
     print(f"{k}: {ms*1e3:7.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
