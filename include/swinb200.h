@@ -116,6 +116,9 @@ int swinb200_colsum(const void* x, int act_dtype, float* out, int rows, int cols
  *   o: (T, C) act in un-rolled token order; lse: (B, nW, heads, L) fp32 log-sum-exp rows.
  * window_attn_bwd: dqkv (T, 3C) act = gradients w.r.t. the *un-normalised* q, k and v;
  *   dscale (heads) += sum dS * cos ; dbias (heads, L, L) += sum_windows dS (nullable).
+ *   ws: optional scratch of T*heads floats (the library allocates nothing).  With it the tcgen05 back end runs its
+ *   persistent kernel (window operands arrive as TMA boxes while the previous window is processed; the row term
+ *   D = <dO, O> comes from a streaming pre-pass into ws); with NULL every window is one self-contained CTA.
  * backend: SWINB200_GEMM_SIMT (CUDA cores, any act dtype) or SWINB200_GEMM_TCGEN05 (bf16). */
 int swinb200_qk_normalize(void* qkv, int act_dtype, float* inv_norm, int T, int C, int heads, void* stream);
 int swinb200_shift_mask(float* mask, int H, int W, int Wh, int Ww, int s0, int s1, void* stream);
@@ -124,8 +127,8 @@ int swinb200_window_attn_fwd(int backend, const void* qkv, int act_dtype, const 
                              int Wh, int Ww, int s0, int s1, void* stream);
 int swinb200_window_attn_bwd(int backend, const void* qkv, int act_dtype, const float* inv_norm,
                              const float* scale, const float* bias, const void* o, const void* d_o,
-                             const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W,
-                             int C, int heads, int Wh, int Ww, int s0, int s1, void* stream);
+                             const float* lse, void* dqkv, float* dscale, float* dbias, float* ws, int B, int H,
+                             int W, int C, int heads, int Wh, int Ww, int s0, int s1, void* stream);
 
 /* ---- latitude-weighted L2 loss ------------------------------------------------------------------------
  * fwd: num[b,c] = sum_hw qw[h] (p-t)^2 ; den[b,c] = sum_hw qw[h] t^2 ;

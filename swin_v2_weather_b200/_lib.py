@@ -33,7 +33,7 @@ PROTOTYPES = {
     "swinb200_qk_normalize": [_P, _I, _P, _I, _I, _I, _P],
     "swinb200_shift_mask": [_P, _I, _I, _I, _I, _I, _I, _P],
     "swinb200_window_attn_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    "swinb200_window_attn_bwd": [_I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "swinb200_window_attn_bwd": [_I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "swinb200_latw_l2_fwd": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     "swinb200_debug_attn_phase_buffer": [_P],
     "swinb200_debug_umma_probe": [_P, _P, _P, _I, _I, _I, _I, _I, _P],

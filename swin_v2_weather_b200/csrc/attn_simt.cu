@@ -316,8 +316,8 @@ static int launch_bwd(const T* qkv, const float* inv_norm, const float* scale, c
 int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, void* o, float* lse, int B, int H, int W, int C,
                      int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream);
 int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale, const float* bias, const void* o,
-                     const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W, int C,
-                     int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream);
+                     const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, float* ws, int B, int H, int W,
+                     int C, int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream);
 
 static int check_geom(const char* who, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
   SWB_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && heads > 0, "%s: bad shape", who);
@@ -350,15 +350,15 @@ extern "C" int swinb200_window_attn_fwd(int backend, const void* qkv, int act_dt
 
 extern "C" int swinb200_window_attn_bwd(int backend, const void* qkv, int act_dtype, const float* inv_norm, const float* scale,
                                         const float* bias, const void* o, const void* d_o, const float* lse, void* dqkv,
-                                        float* dscale, float* dbias, int B, int H, int W, int C, int heads, int Wh, int Ww,
-                                        int s0, int s1, void* stream) {
+                                        float* dscale, float* dbias, float* ws, int B, int H, int W, int C, int heads, int Wh,
+                                        int Ww, int s0, int s1, void* stream) {
   SWB_CHECK_ARG(qkv && inv_norm && scale && o && d_o && lse && dqkv && dscale, "window_attn_bwd: null pointer");
   if (int e = check_geom("window_attn_bwd", B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
   const WinGeom g{B, H, W, C, heads, Wh, Ww, s0, s1};
   cudaStream_t s = (cudaStream_t)stream;
   if (backend == SWINB200_GEMM_TCGEN05) {
     SWB_CHECK_ARG(act_dtype == SWINB200_BF16, "window_attn_bwd: the tcgen05 back end needs bf16 activations");
-    return attn_tcgen05_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, dqkv, dscale, dbias, B, H, W, C, heads, Wh, Ww, s0, s1, s);
+    return attn_tcgen05_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, dqkv, dscale, dbias, ws, B, H, W, C, heads, Wh, Ww, s0, s1, s);
   }
   SWB_CHECK_ARG(backend == SWINB200_GEMM_SIMT, "window_attn_bwd: unknown backend %d", backend);
   if (act_dtype == SWINB200_BF16)

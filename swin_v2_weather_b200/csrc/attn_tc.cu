@@ -1108,13 +1108,44 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
 }
 
+// Persistent variant: shared-memory layout with a 128-byte-aligned chunk stride so every (operand, 16-byte chunk) column
+// of a window is one TMA box [8 elements x Ww x Wh] of the (B, H, W, channels) activation tensor.
+template <int D>
+struct Bwd2Smem {
+  static constexpr int kChunks = D / 8;
+  static constexpr int kCS = kMaxLP * 16;                        // 2816 = 22 * 128
+  static constexpr int kTile = kChunks * kCS;
+  static constexpr int kPCS = 128 * 16;
+  static constexpr int kPTile = (kMaxLP / 8) * kPCS;
+  static constexpr int kOffQ = 0, kOffK = kTile, kOffV = 2 * kTile, kOffG = 3 * kTile;   // G = dO
+  static constexpr int kOffP = 4 * kTile, kOffDS = kOffP + kPTile;
+  static constexpr int kOffTok = kOffDS + kPTile;
+  static constexpr int kOffLse = kOffTok + kMaxLP * 4;
+  static constexpr int kOffDv = kOffLse + kMaxLP * 4;
+  static constexpr int kOffRed = kOffDv + kMaxLP * 4;
+  static constexpr int kOffBar = kOffRed + 64;
+  static constexpr int kOffTok2 = kOffBar + 64;                  // next item's token table
+  static constexpr int kOffDsc = kOffTok2 + kMaxLP * 4;          // per-head d(scale) partials
+  static constexpr int kBytes = kOffDsc + 128;
+  static_assert(kBytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 template <int D>
 __global__ void __launch_bounds__(256, 1)
-attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ inv_norm, const float* __restrict__ scale_p,
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const float* __restrict__ Dpre,
+                   const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ inv_norm, const float* __restrict__ scale_p,
                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dscale,
                    float* __restrict__ dbias, const AttnGeom g) {
-  using SM = BwdSmem<D>;
+  using SM = Bwd2Smem<D>;
   constexpr float kLog2e = 1.4426950408889634f;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sQ = smem + SM::kOffQ;
@@ -1127,8 +1158,9 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   float* lse2 = reinterpret_cast<float*>(smem + SM::kOffLse);   // log2-domain LSE per query (+inf for pad queries)
   float* Dv = reinterpret_cast<float*>(smem + SM::kOffDv);      // rowsum(dO o O) per query
   float* red = reinterpret_cast<float*>(smem + SM::kOffRed);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::kOffBar);     // MMA completion
+  uint64_t* ld_bar = bar + 1;                                          // operand boxes of the next item have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long ph_acc[12];
@@ -1144,7 +1176,10 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 
   // ---- one-time set-up: barrier, tensor memory, zero pad rows (gathers only ever write rows < L) -------------------
   if (tid == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_do);
     mbar_init(bar, 1);
+    mbar_init(ld_bar, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -1177,9 +1212,41 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     }
     return hd;
   };
-  if ((int)blockIdx.x < nitems) fill_tok(blockIdx.x, tokbuf[0]);
+  // A window whose rows or columns wrap around the cyclic shift is not one box of the tensor: those items (the last
+  // window row / column of the shifted blocks, ~10 % of them) keep the per-thread cp.async gather.
+  auto item_is_box = [&](int item) {
+    const int ww_all = (item / g.heads) % g.nW;
+    const int wh = ww_all / g.nWw, ww = ww_all - wh * g.nWw;
+    return !((g.s0 > 0 && (wh + 1) * g.Wh + g.s0 > g.H) || (g.s1 > 0 && (ww + 1) * g.Ww + g.s1 > g.W));
+  };
+  constexpr uint32_t kBoxBytes = 16;   // x L rows, per (operand, chunk)
+  // one thread: boxes of operands [op_lo, op_hi) of `item`; `first` registers the item's total byte count
+  auto issue_boxes = [&](int op_lo, int op_hi, int item, bool first) {
+    const int hd = item % g.heads;
+    const int ww_all = (item / g.heads) % g.nW;
+    const int bb = item / (g.heads * g.nW);
+    const int wh = ww_all / g.nWw, ww = ww_all - wh * g.nWw;
+    fence_proxy_async_smem();    // earlier generic-proxy reads of these tiles are ordered before the async-proxy writes
+    if (first) mbar_arrive_expect_tx(ld_bar, 4u * SM::kChunks * kBoxBytes * (uint32_t)L);
+    for (int op = op_lo; op < op_hi; ++op) {
+      const CUtensorMap* tm = (op < 3) ? &tm_qkv : &tm_do;
+      const int chunk0 = ((op < 3) ? op * C + hd * D : hd * D) / 8;
+#pragma unroll 4
+      for (int c = 0; c < SM::kChunks; ++c)
+        tma_load_5d(smem + op * SM::kTile + c * SM::kCS, tm, ld_bar, 0, chunk0 + c, ww * g.Ww + g.s1, wh * g.Wh + g.s0, bb);
+    }
+  };
+  bool cur_box = false;
+  uint32_t ld_parity = 0;
+  if ((int)blockIdx.x < nitems) {
+    fill_tok(blockIdx.x, tokbuf[0]);
+    cur_box = item_is_box(blockIdx.x);
+  }
   __syncthreads();
-  if ((int)blockIdx.x < nitems) gather(0, 4, tokbuf[0], (int)blockIdx.x % g.heads);
+  if ((int)blockIdx.x < nitems) {
+    if (cur_box) { if (tid == 0) issue_boxes(0, 4, blockIdx.x, true); }
+    else gather(0, 4, tokbuf[0], (int)blockIdx.x % g.heads);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1200,6 +1267,7 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   const int item_next = item + gridDim.x;
   const bool has_next = item_next < nitems;
   const int head_next = has_next ? fill_tok(item_next, tok_next) : 0;    // visible after the next barrier
+  const bool next_box = has_next && item_is_box(item_next);
   int label_split = LP;
   if (shifted) {
     const int wh = w / g.nWw;
@@ -1210,12 +1278,20 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
       label_split = 0;
     }
   }
-  for (int n = tid; n < LP; n += 256)
+  for (int n = tid; n < LP; n += 256) {
     lse2[n] = (n < L) ? lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] * kLog2e : INFINITY;
+    Dv[n] = (n < L) ? Dpre[(size_t)tok[n] * g.heads + head] : 0.f;      // D_n = <dO_n, O_n> (pre-pass kernel)
+  }
   const float scale = scale_p[head];
   const float scale_l2 = scale * kLog2e;
-  cp_async_wait_all();            // this item's operands (gathered during the previous item, or just above)
-  fence_proxy_async_smem();
+  // this item's operands: TMA boxes issued during the previous item (or just above), or the cp.async gather
+  if (cur_box) {
+    mbar_wait(ld_bar, ld_parity, 640);
+    ld_parity ^= 1;
+  } else {
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   SWB_ACC(2);
@@ -1242,26 +1318,6 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
         umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(g0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
                      umma_desc_nosw(v0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
       umma_commit(bar);
-    }
-    if (t == 0) {
-      // D_n = <dO_n, O_n> for every query of the window, while the first MMAs run
-      for (int n = tid; n < LP; n += 256) {
-        float acc = 0.f;
-        if (n < L) {
-          const __nv_bfloat16* go = d_o + (size_t)tok[n] * C + head * D;
-          const __nv_bfloat16* oo = o + (size_t)tok[n] * C + head * D;
-#pragma unroll
-          for (int c = 0; c < D; c += 8) {
-            float a8[8], b8[8];
-            ld8(go + c, a8);
-            ld8(oo + c, b8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc = fmaf(a8[e], b8[e], acc);
-          }
-        }
-        Dv[n] = acc;
-      }
-      __syncthreads();
     }
     mbar_wait(bar, parity, 600 + t);
     SWB_ACC(3);
@@ -1422,7 +1478,10 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     parity ^= 1;
     tc_fence_after();
     // K^ and V have served their last MMA of this item: start gathering the next item's K^ / V into them
-    if (u == ntiles - 1 && has_next) gather(1, 3, tok_next, head_next);
+    if (u == ntiles - 1 && has_next) {
+      if (next_box) { if (tid == 0) issue_boxes(1, 3, item_next, true); }
+      else gather(1, 3, tok_next, head_next);
+    }
     {
       const int jk = u * 128 + r;                       // key slot of this thread
       const bool key_ok = jk < L;
@@ -1488,8 +1547,12 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
     tc_fence_after();
     // ... and Q^ / dO after the last dV / dK^ MMAs
     if (u == ntiles - 1 && has_next) {
-      gather(0, 1, tok_next, head_next);
-      gather(3, 4, tok_next, head_next);
+      if (next_box) {
+        if (tid == 0) { issue_boxes(0, 1, item_next, false); issue_boxes(3, 4, item_next, false); }
+      } else {
+        gather(0, 1, tok_next, head_next);
+        gather(3, 4, tok_next, head_next);
+      }
     }
     const int rows_here = min(128, L - u * 128);
     {
@@ -1541,6 +1604,7 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   // ---- d(scale) = sum dS o cos: per-warp partial -> per-head slot of this CTA ------------------------------------------
   dsc_acc = warp_sum(dsc_acc);
   if (lane == 0) atomicAdd(&dsc_heads[head], dsc_acc);
+  cur_box = next_box;
   }   // item loop
   __syncthreads();
   if (tid < g.heads) {
@@ -1556,35 +1620,97 @@ attn_tc_bwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   }
 }
 
+// D[t, h] = <dO[t, h, :], O[t, h, :]>  (the softmax-backward row term), four lanes per (token, head)
+__global__ void __launch_bounds__(256) attn_rowdot_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                                          float* __restrict__ out, long long n_pairs, int d) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pair = gid >> 2;
+  const int q = (int)(gid & 3);
+  float acc = 0.f;
+  if (pair < n_pairs) {
+    const __nv_bfloat16* a = o + pair * d;
+    const __nv_bfloat16* b = d_o + pair * d;
+    for (int c = q * 8; c < d; c += 32) {
+      float a8[8], b8[8];
+      ld8(a + c, a8);
+      ld8(b + c, b8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(a8[e], b8[e], acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (q == 0 && pair < n_pairs) out[pair] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// (B, H, W, channels) bf16 activation seen as [8 | channels/8 | W | H | B]; one box = the 16-byte chunk column of a window
+static int make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int channels, int Wh, int Ww) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SWINB200_ERR_CUDA;
+  }
+  const cuuint64_t row = (cuuint64_t)channels * 2;
+  cuuint64_t dims[5] = {8, (cuuint64_t)channels / 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[4] = {16, row, row * W, row * W * H};
+  cuuint32_t box[5] = {8, 1, (cuuint32_t)Ww, (cuuint32_t)Wh, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (window map) failed (%d)", (int)r);
+    return SWINB200_ERR_CUDA;
+  }
+  return SWINB200_OK;
+}
+
+// ws: optional workspace of B*H*W*heads floats.  With it the persistent kernel runs (operands arrive as TMA boxes while the
+// previous window is still being processed, D = <dO, O> comes from a streaming pre-pass); without it the one-CTA-per-window
+// kernel does everything in place.
 int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale, const float* bias, const void* o,
-                     const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, int B, int H, int W, int C,
-                     int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
+                     const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, float* ws, int B, int H, int W,
+                     int C, int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
   AttnGeom g;
   if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
-  using SM = BwdSmem<96>;
-  static bool configured = false;
-  if (!configured) {
-    SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
-  }
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_BWD");
-    variant = e ? atoi(e) : 1;   // 2 = persistent kernel with in-place prefetch (experimental, not faster yet)
+    variant = e ? atoi(e) : 2;   // 1 = one CTA per (window, head);  2 = persistent CTAs fed by TMA boxes (needs ws)
   }
-  if (variant == 1) {
+  const bool aligned = ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)d_o % 16 == 0);
+  if (variant == 1 || ws == nullptr || !aligned) {
+    using SM = BwdSmem<96>;
+    static bool configured = false;
+    if (!configured) {
+      SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+      configured = true;
+    }
     attn_tc_bwd_kernel<96><<<B * g.nW * heads, 256, SM::kBytes, stream>>>(
         (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
         (__nv_bfloat16*)dqkv, dscale, dbias, g);
   } else {
+    using SM = Bwd2Smem<96>;
     static bool configured2 = false;
     if (!configured2) {
       SWB_CUDA(cudaFuncSetAttribute(attn_tc_bwd2_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
       configured2 = true;
     }
+    CUtensorMap tm_qkv, tm_do;
+    if (int e = make_window_tmap(&tm_qkv, qkv, B, H, W, 3 * C, Wh, Ww)) return e;
+    if (int e = make_window_tmap(&tm_do, d_o, B, H, W, C, Wh, Ww)) return e;
+    const long long n_pairs = (long long)B * H * W * heads;
+    attn_rowdot_kernel<<<(unsigned)((n_pairs * 4 + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
+                                                                                  ws, n_pairs, C / heads);
+    SWB_LAUNCH_CHECK();
     const int grid = min(B * g.nW * heads, sm_count());
     attn_tc_bwd2_kernel<96><<<grid, 256, SM::kBytes, stream>>>(
-        (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
+        tm_qkv, tm_do, ws, (const __nv_bfloat16*)qkv, inv_norm, scale, bias, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse,
         (__nv_bfloat16*)dqkv, dscale, dbias, g);
   }
   SWB_LAUNCH_CHECK();

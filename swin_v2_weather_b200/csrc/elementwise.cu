@@ -732,9 +732,193 @@ extern "C" int swinb200_ln_residual_fwd(const void* z, int act_dtype, const floa
   SWB_CHECK_ARG(false, "ln_residual_fwd: bad act_dtype %d", act_dtype);
 }
 
+// ---- bf16 fast path for C = 128*NK channels (the model's C = 768) ---------------------------------------------------
+// One producer warp keeps a 3-stage ring of 8-row tiles (dx fp32 + z bf16, two cp.async.bulk per tile) in flight; each of
+// the 8 consumer warps owns one row of every tile and does the whole row from registers: lane l holds channels
+// {l*4 + 128*k + e} (conflict-free 16-byte / 8-byte shared loads), two warp reductions give the row means, dz goes to the
+// warp's own staging row and leaves with a 1.5 KB cp.async.bulk store.  No CTA-wide barrier in the loop; the ring slot is
+// released as soon as the row sits in registers.  Per-channel sums (dgamma, dbeta, bias gradient of the previous Linear)
+// stay in registers, are folded through shared memory once per CTA and reach HBM as one atomic per channel per CTA.
+constexpr int kLnbRows = 8, kLnbStages = 3, kLnbThreads = 32 * (kLnbRows + 1);
+__device__ __forceinline__ void lnb_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+template <int NK>
+struct LnbSmem {
+  static constexpr int C = 128 * NK;
+  static constexpr int kDx = kLnbRows * C * 4, kZ = kLnbRows * C * 2, kStage = kDx + kZ;
+  static constexpr int kOffOut = kLnbStages * kStage;                 // [warp][2][C] bf16
+  static constexpr int kOffRed = kOffOut + kLnbRows * 2 * C * 2;      // [3][C] fp32
+  static constexpr int kOffBar = kOffRed + 3 * C * 4;
+  static constexpr int kBytes = kOffBar + 64;
+};
+
+template <int NK>
+__global__ void __launch_bounds__(kLnbThreads, 1)
+ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ sample_scale, __nv_bfloat16* __restrict__ dz,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev, int rows,
+                      int rows_per_sample) {
+  using SM = LnbSmem<NK>;
+  constexpr int C = SM::C;
+  extern __shared__ __align__(128) unsigned char lsm[];
+  float* red = reinterpret_cast<float*>(lsm + SM::kOffRed);
+  uint64_t* full = reinterpret_cast<uint64_t*>(lsm + SM::kOffBar);   // [stages]
+  uint64_t* empty = full + kLnbStages;                                // [stages]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (rows + kLnbRows - 1) / kLnbRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kLnbStages; ++s) {
+      lnb_mbar_init(&full[s], 1);
+      lnb_mbar_init(&empty[s], kLnbRows);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 3 * C; i += kLnbThreads) red[i] = 0.f;
+  __syncthreads();
+
+  if (warp == kLnbRows) {
+    // ------------------------------------------------ producer ------------------------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % kLnbStages;
+        if (it >= kLnbStages) lnb_mbar_wait(&empty[stage], (uint32_t)((it / kLnbStages - 1) & 1));
+        const int r0 = tile * kLnbRows;
+        const int nr = min(kLnbRows, rows - r0);
+        unsigned char* st = lsm + stage * SM::kStage;
+        lnb_mbar_expect(&full[stage], (uint32_t)(nr * C * 6));
+        bulk_load(st, dx + (size_t)r0 * C, (uint32_t)(nr * C * 4), &full[stage]);
+        bulk_load(st + SM::kDx, z + (size_t)r0 * C, (uint32_t)(nr * C * 2), &full[stage]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ consumers: warp w <-> row w of every tile ----------------------
+    float gm[NK][4], a_g[NK][4], a_b[NK][4], a_z[NK][4];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * k));
+      gm[k][0] = g4.x; gm[k][1] = g4.y; gm[k][2] = g4.z; gm[k][3] = g4.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { a_g[k][e] = 0.f; a_b[k][e] = 0.f; a_z[k][e] = 0.f; }
+    }
+    unsigned char* obuf = lsm + SM::kOffOut + warp * 2 * C * 2;
+    const float invC = 1.0f / (float)C;
+    int it = 0, nstores = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int stage = it % kLnbStages;
+      const int row = tile * kLnbRows + warp;
+      const bool active = row < rows;
+      float mean = 0.f, rstd = 0.f, sc = 1.f;
+      if (active) {     // issued before the wait: the latency hides behind the tile's arrival
+        mean = __ldg(stats + 2 * (size_t)row);
+        rstd = __ldg(stats + 2 * (size_t)row + 1);
+        if (sample_scale) sc = __ldg(sample_scale + row / rows_per_sample);
+      }
+      lnb_mbar_wait(&full[stage], (uint32_t)((it / kLnbStages) & 1));
+      float d[NK][4], zv[NK][4];
+      if (active) {
+        const unsigned char* st = lsm + stage * SM::kStage;
+        const float4* dxr = reinterpret_cast<const float4*>(st + (size_t)warp * C * 4);
+        const uint2* zr = reinterpret_cast<const uint2*>(st + SM::kDx + (size_t)warp * C * 2);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const float4 d4 = dxr[lane + 32 * k];
+          const uint2 z2 = zr[lane + 32 * k];
+          d[k][0] = d4.x; d[k][1] = d4.y; d[k][2] = d4.z; d[k][3] = d4.w;
+          zv[k][0] = __uint_as_float(z2.x << 16); zv[k][1] = __uint_as_float(z2.x & 0xffff0000u);
+          zv[k][2] = __uint_as_float(z2.y << 16); zv[k][3] = __uint_as_float(z2.y & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) lnb_mbar_arrive(&empty[stage]);      // the row is in registers: the slot may be refilled
+      if (!active) continue;
+      float A = 0.f, Bq = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float g = d[k][e] * gm[k][e];
+          A += g;
+          Bq = fmaf(g, zv[k][e], Bq);
+        }
+      A = warp_sum(A);
+      Bq = warp_sum(Bq);
+      const float xo = -mean * rstd;                          // xhat = z * rstd + xo
+      const float mg = sc * A * invC;                         // mean_c(g),  g = dx*sc*gamma
+      const float mgx = sc * rstd * (Bq - mean * A) * invC;   // mean_c(g * xhat)
+      unsigned char* ob = obuf + (nstores & 1) * C * 2;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two rows ago has drained
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        float o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float du = d[k][e] * sc;
+          const float xh = fmaf(zv[k][e], rstd, xo);
+          o4[e] = rstd * (fmaf(du, gm[k][e], -mg) - xh * mgx);
+          a_b[k][e] += du;
+          a_g[k][e] = fmaf(du, xh, a_g[k][e]);
+          a_z[k][e] += o4[e];
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(o4[0], o4[1]);
+        pk.y = pack_bf16x2(o4[2], o4[3]);
+        reinterpret_cast<uint2*>(ob)[lane + 32 * k] = pk;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(dz + (size_t)row * C, ob, (uint32_t)(C * 2));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      ++nstores;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = lane * 4 + 128 * k + e;
+        atomicAdd(red + c, a_g[k][e]);
+        atomicAdd(red + C + c, a_b[k][e]);
+        atomicAdd(red + 2 * C + c, a_z[k][e]);
+      }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kLnbThreads) {
+    atomicAdd(dgamma + c, red[c]);
+    atomicAdd(dbeta + c, red[C + c]);
+    if (dbias_prev) atomicAdd(dbias_prev + c, red[2 * C + c]);
+  }
+}
+
+template <int NK>
+static int launch_ln_bwd_rowwarp(const float* dx, const __nv_bfloat16* z, const float* stats, const float* gamma, const float* ss,
+                                 __nv_bfloat16* dz, float* dgamma, float* dbeta, float* dbias_prev, int rows, int rps,
+                                 cudaStream_t s) {
+  using SM = LnbSmem<NK>;
+  static bool configured = false;
+  if (!configured) {
+    SWB_CUDA(cudaFuncSetAttribute(ln_bwd_rowwarp_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  const int ntiles = (rows + kLnbRows - 1) / kLnbRows;
+  ln_bwd_rowwarp_kernel<NK><<<max(1, min(ntiles, sm_count())), kLnbThreads, SM::kBytes, s>>>(dx, z, stats, gamma, ss, dz, dgamma,
+                                                                                           dbeta, dbias_prev, rows, rps);
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
+}
+
 template <typename T>
 static int launch_ln_bwd(const float* dx, const T* z, const float* stats, const float* gamma, const float* ss, T* dz,
                          float* dgamma, float* dbeta, float* dbias_prev, int rows, int C, int rps, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {
+    const bool aligned = ((uintptr_t)dx % 16 == 0) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)dz % 16 == 0) && ((uintptr_t)gamma % 16 == 0);
+    if (C == 768 && aligned) return launch_ln_bwd_rowwarp<6>(dx, z, stats, gamma, ss, dz, dgamma, dbeta, dbias_prev, rows, rps, s);
+  }
   if (C / 8 > 256) {
     set_error("ln_residual_bwd: C=%d > 2048 unsupported", C);
     return SWINB200_ERR_UNSUPPORTED;

@@ -259,11 +259,13 @@ def window_attn_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, B, H, W, C, heads, 
     if dscale is None:
         dscale = torch.zeros((heads,), dtype=torch.float32, device=qkv.device)
     dbias = torch.zeros((heads, L, L), dtype=torch.float32, device=qkv.device) if bias is not None else None
+    # scratch for the row term D = <dO, O> (tcgen05 back end: enables the persistent kernel)
+    ws = torch.empty((qkv.shape[0] * heads,), dtype=torch.float32, device=qkv.device) if backend == BACKEND_TCGEN05 else None
     _lib.call("swinb200_window_attn_bwd", backend, _chk(qkv, "qkv"), _code(qkv.dtype),
               _chk(inv_norm, "inv_norm", torch.float32), _chk(scale, "scale", torch.float32),
               _chk(bias, "bias", torch.float32, True), _chk(o, "o", qkv.dtype), _chk(d_o, "d_o", qkv.dtype),
               _chk(lse, "lse", torch.float32), dqkv.data_ptr(), dscale.data_ptr(), 0 if dbias is None else dbias.data_ptr(),
-              B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
+              0 if ws is None else ws.data_ptr(), B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
     return dqkv, dscale, dbias
 
 

@@ -88,6 +88,28 @@ def test_transpose_and_pos_grad():
     assert rel(got, dx.sum(0).t()) < 1e-6
 
 
+def test_ln_residual_bwd_ring_kernel():
+    """C = 768 / bf16 takes the warp-per-row ring kernel: more tiles than CTAs x stages, and a ragged last tile."""
+    C, B, rps = 768, 2, 8 * 148 * 2 + 3
+    rows = B * rps
+    z = gen(rows, C, seed=16).to(torch.bfloat16)
+    gamma, beta = 1 + 0.1 * gen(C, seed=17), 0.1 * gen(C, seed=18)
+    ss = torch.tensor([1.0 / 0.8, 0.0], device=DEV)
+    dx = gen(rows, C, seed=19)
+    for use_ss in (False, True):
+        _, _, stats = ops.ln_residual_fwd(z, None, gamma, beta, ss if use_ss else None, None, rps, ops.MODE_BF16)
+        dz, dg, db, dbp = ops.ln_residual_bwd(dx, z, stats, gamma, ss if use_ss else None, rps, ops.MODE_BF16)
+        zf = z.float().clone().requires_grad_(True)
+        gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        u = torch.nn.functional.layer_norm(zf, (C,), gf, bf, 1e-5)
+        if use_ss:
+            u = u * ss.repeat_interleave(rps).view(-1, 1)
+        u.backward(dx)
+        assert rel(dz, zf.grad) < TOL[torch.bfloat16]
+        assert rel(dg, gf.grad) < 1e-5 and rel(db, bf.grad) < 1e-5
+        assert rel(dbp, zf.grad.sum(0)) < 1e-4      # sum of bf16-rounded dz vs fp32 reference rows
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C", [96, 192, 768])
 def test_ln_residual_fwd_bwd(dtype, C):
