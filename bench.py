@@ -94,7 +94,10 @@ class ClockSampler:
 # ---- kernel-family timer (CUDA events on the launching stream, no syncs inside the timed region) ------------------
 class KernelTimer:
     FAMILY = {"swinb200_gemm": "gemm", "swinb200_window_attn_fwd": "attn_fwd", "swinb200_window_attn_bwd": "attn_bwd",
-              "swinb200_ln_residual_fwd": "ln_fwd", "swinb200_ln_residual_bwd": "ln_bwd"}
+              "swinb200_ln_residual_fwd": "ln_fwd", "swinb200_ln_residual_bwd": "ln_bwd", "swinb200_colsum": "colsum",
+              "swinb200_patchify": "patchify", "swinb200_unpatchify": "unpatchify", "swinb200_latw_l2_fwd": "loss",
+              "swinb200_latw_l2_bwd": "loss", "swinb200_transpose_f32": "transpose", "swinb200_pos_embed_grad": "transpose",
+              "swinb200_cast_f32_to_bf16": "cast"}
 
     def __init__(self):
         self.records = []   # (family, flops, bytes, start_event, end_event)

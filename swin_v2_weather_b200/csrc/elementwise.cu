@@ -53,6 +53,36 @@ __global__ void transpose_sum_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// 64 x 64 tiles with 128-bit global accesses on both sides (R and Cc multiples of 4, 16-byte aligned pointers)
+__global__ void __launch_bounds__(256) transpose_sum_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int nb,
+                                                                int R, int Cc) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = r0 + ty + 16 * j, c = c0 + tx * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R && c < Cc)
+      for (int b = 0; b < nb; ++b) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * R + r) * Cc + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    float* t = &tile[ty + 16 * j][tx * 4];
+    t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 16 * j, r = r0 + tx * 4;
+    if (r < R && c < Cc) {
+      const int cc = ty + 16 * j;
+      *reinterpret_cast<float4*>(dst + (size_t)c * R + r) =
+          make_float4(tile[tx * 4][cc], tile[tx * 4 + 1][cc], tile[tx * 4 + 2][cc], tile[tx * 4 + 3][cc]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // patchify / unpatchify
 // ------------------------------------------------------------------------------------------------
@@ -434,7 +464,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (c < cols) {
-    for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+    // four independent 16-byte loads in flight per thread: the pass is pure HBM streaming
+    const int step = gridDim.y * 8;
+    int r = blockIdx.y * 8 + ty;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      float v0[8], v1[8], v2[8], v3[8];
+      ld8(x + (size_t)r * ld + c, v0);
+      ld8(x + (size_t)(r + step) * ld + c, v1);
+      ld8(x + (size_t)(r + 2 * step) * ld + c, v2);
+      ld8(x + (size_t)(r + 3 * step) * ld + c, v3);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+    }
+    for (; r < rows; r += step) {
       float v[8];
       ld8(x + (size_t)r * ld + c, v);
 #pragma unroll
@@ -630,8 +672,13 @@ extern "C" int swinb200_cast_f32_to_bf16(const float* src, void* dst, size_t n, 
 
 extern "C" int swinb200_pos_embed_grad(const float* dx, float* dpos, int B, int rows_per_sample, int C, void* stream) {
   SWB_CHECK_ARG(dx && dpos && B > 0 && rows_per_sample > 0 && C > 0, "pos_embed_grad: bad arguments");
-  dim3 grid((rows_per_sample + 31) / 32, (C + 31) / 32), block(32, 8);
-  transpose_sum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dx, dpos, B, rows_per_sample, C);
+  if (rows_per_sample % 4 == 0 && C % 4 == 0 && (uintptr_t)dx % 16 == 0 && (uintptr_t)dpos % 16 == 0) {
+    dim3 grid((rows_per_sample + 63) / 64, (C + 63) / 64);
+    transpose_sum_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dx, dpos, B, rows_per_sample, C);
+  } else {
+    dim3 grid((rows_per_sample + 31) / 32, (C + 31) / 32), block(32, 8);
+    transpose_sum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dx, dpos, B, rows_per_sample, C);
+  }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
 }

@@ -165,8 +165,8 @@ class SwinBlockFn(torch.autograd.Function):
         # ---- MLP branch: x_out = x_mid + dp2 * LN2(fc2(gelu(fc1(xb_mid))))
         dz2, dg2, db2, dbias_fc2 = ops.ln_residual_bwd(dx_out, z2, st2, n2_w.detach(), dp2, H * W, mode, acc=acc["ln2"].view(3, C))
         dh = ops.gemm(mode, dz2, 0, w2, 1, EPI_DGELU, aux=h)                                     # (T, hidden)
+        dbias_fc1 = ops.colsum(dh, out=acc["b_fc1"])          # right behind the GEMM that wrote dh: its tail is still in L2
         dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
-        dbias_fc1 = ops.colsum(dh, out=acc["b_fc1"])
         dx_mid = ops.gemm(mode, dh, 0, w1, 1, EPI_ADD_F32, aux=dx_out)                           # fp32 (T, C)
         dw_fc1 = wgrad(dh, xb_mid, hid, C, "w_fc1")
         del dh

@@ -81,8 +81,9 @@ def test_unpatchify_is_adjoint_of_patchify(dtype):
 
 
 def test_transpose_and_pos_grad():
-    src = gen(650, 200, seed=4)
-    assert torch.equal(ops.transpose_f32(src), src.t().contiguous())
+    for shape in ((650, 200), (652, 200), (64, 64), (1300, 772)):     # scalar kernel / 128-bit kernel with ragged tiles
+        src = gen(*shape, seed=4)
+        assert torch.equal(ops.transpose_f32(src), src.t().contiguous())
     dx = gen(3, 648, 96, seed=5)
     got = ops.pos_embed_grad(dx.view(3 * 648, 96), 3, 648, 96)
     assert rel(got, dx.sum(0).t()) < 1e-6
