@@ -10,6 +10,10 @@
 // highest warp id, and the MMA loop is latency-critical (its ~40 instructions per k-block must not queue behind the
 // epilogue warps' arithmetic, which is what capped the GELU GEMMs at 54 % tensor-pipe activity).  Both loops run
 // warp-convergent with the issuing lane elected per instruction, so descriptors live in uniform registers.
+// Tile scheduling (CTA pairs): the grid has one cluster per output tile; the 74 resident clusters keep their TMEM,
+// barriers and pipeline state and obtain further tiles by cancelling pending clusters (clusterlaunchcontrol.try_cancel),
+// one query ahead of the producer.  SMs that are busy with another kernel (NCCL's all-reduce CTAs during the backward of
+// a data-parallel step) simply take no tiles, instead of stalling a static round-robin schedule until they are free.
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
 // token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
@@ -195,6 +199,30 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// ---- cluster launch control: a running cluster cancels a not-yet-launched cluster of the same grid and takes over its
+// block index.  The 16-byte response is multicast to the same shared-memory offset of every CTA of the cluster and
+// completes 16 bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void clc_try_cancel(void* resp, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+      : "memory");
+}
+// -> blockIdx.x of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(const void* resp) {
+  uint32_t ok = 0, x = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+      : "+r"(x), "=r"(ok)
+      : "r"(smem_u32(resp))
+      : "memory");
+  return ok ? (int)x : -1;
+}
+
 // 16-byte chunk `c` (0..3) of the 64-byte staging row `r`, 64B-swizzled exactly as the TMA store expects
 // (address bits [4,6) ^= bits [7,9)); eight consecutive rows land in eight distinct 16-byte bank groups.
 __device__ __forceinline__ unsigned char* staging_chunk(unsigned char* buf, int r, int c) {
@@ -222,6 +250,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  static_assert((2 * Cfg::kStages + 4) * 8 + 4 <= 128, "pipeline barriers overflow their 128 bytes");
+  constexpr int kSched = 4;                                                           // tile-id ring (CLC responses)
+  unsigned char* clc_resp = smem + Cfg::kOffBars + 128;                               // [kSched] x 16 bytes
+  uint64_t* sfull = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars + 192);          // [kSched] response has landed
+  uint64_t* sempty = sfull + kSched;                                                  // [kSched] every role has read it (leader's copy)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -238,7 +271,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], (PAIR ? 2 : 1) * 4 * kEpiGroups);   // PAIR: both CTAs' epilogue warps report to the leader
     }
+    if (PAIR) {
+      for (int q = 0; q < kSched; ++q) {
+        mbar_init(&sfull[q], 1);
+        mbar_init(&sempty[q], 2 * (1 + 4 * kEpiGroups) + 1);       // producer + epilogue warps of both CTAs, MMA warp
+      }
+    }
     fence_barrier_init();
+    if (PAIR)
+      for (int q = 0; q < kSched; ++q) mbar_arrive_expect_tx(&sfull[q], 16);   // armed for the first kSched responses
   }
   if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
@@ -251,12 +292,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  // tile after the i-th one this role has processed (-1: none).  Called by whole, converged warps.
+  auto next_tile = [&](int tile, int i, bool rearm) -> int {
+    if (!PAIR) {
+      const int t = tile + cta_stride;
+      return t < num_tiles ? t : -1;
+    }
+    const int q = i & (kSched - 1);
+    mbar_wait(&sfull[q], (uint32_t)((i / kSched) & 1), 700 + q);
+    const int bid = clc_decode(clc_resp + q * 16);
+    fence_proxy_async_smem();                       // the read is ordered before the next asynchronous overwrite
+    if (rearm && elect_one()) mbar_arrive_expect_tx(&sfull[q], 16);   // this CTA's barrier, for response i + kSched
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(&sempty[q]);
+    return bid < 0 ? -1 : (bid >> 1);
+  };
 
   if (warp == kProducerWarp) {
     // =============================== TMA producer (warp-convergent, one elected lane issues) ====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+    int local = 0;
+    for (int tile = cta_first; tile >= 0; tile = next_tile(tile, local, true), ++local) {
+      if (PAIR && crank == 0) {
+        // scheduler: ask for the tile after this one while this one's loads are issued
+        const int q = local & (kSched - 1);
+        if (local >= kSched) mbar_wait(&sempty[q], (uint32_t)((local / kSched - 1) & 1), 720 + q);
+        if (elect_one()) clc_try_cancel(clc_resp + q * 16, &sfull[q]);
+        __syncwarp();
+      }
       const int ks = tile % p.split_k;
       const int rest = tile / p.split_k;
       const int n0 = (rest % p.num_n_tiles) * BN + (int)crank * BNL;            // PAIR: this CTA's half of the B columns
@@ -311,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++local) {
+      for (int tile = cta_first; tile >= 0; tile = next_tile(tile, local, false), ++local) {
         const int ks = tile % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -359,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_bias = kBiasEpi && p.bias != nullptr;
     const int mrow0 = quarter * 32;        // first tile row of this warp
     int local = 0;
-    for (int tile = cta_first; tile < num_tiles; tile += cta_stride, ++local) {
+    for (int tile = cta_first; tile >= 0; tile = next_tile(tile, local, false), ++local) {
       const int rest = tile / p.split_k;
       const int n0 = (rest % p.num_n_tiles) * BN;
       const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
@@ -627,7 +691,7 @@ static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     kern<<<grid, kGemmThreads, Cfg::kSmem, s>>>(tmA, tmB, tmD, tmD2, p);
   } else {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * min(tiles, sm_count() / 2));
+    cfg.gridDim = dim3(2 * tiles);      // one cluster per tile; resident clusters cancel and absorb the pending ones
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmem;
     cfg.stream = s;
