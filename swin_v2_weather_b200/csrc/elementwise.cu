@@ -878,8 +878,11 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
           zv[k][2] = __uint_as_float(z2.y << 16); zv[k][3] = __uint_as_float(z2.y & 0xffff0000u);
         }
       }
+      // the row is in registers: the slot may be refilled.  The refill is an async-proxy write after these generic-proxy
+      // reads, hence the proxy fence ahead of the release.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) lnb_mbar_arrive(&empty[stage]);      // the row is in registers: the slot may be refilled
+      if (lane == 0) lnb_mbar_arrive(&empty[stage]);
       if (!active) continue;
       float A = 0.f, Bq = 0.f;
 #pragma unroll
