@@ -467,6 +467,47 @@ def test_gemm_tcgen05_qkv_projection_fused_normalise(T, C, heads):
     assert rel(qkv, qkv2) < 6e-3 and rel(inv, inv2) < 3e-3
 
 
+@pytest.mark.parametrize("name", ["fc1_gelu", "fc2", "dgelu", "qkv_dgrad", "fc1_wgrad"])
+def test_gemm_tcgen05_model_shapes(name):
+    """The model's own shapes (T = 64,800 tokens): 3,042 output tiles per launch, i.e. ~40 tiles per resident CTA pair
+    obtained through cluster-launch-control work stealing.  Reference: fp32 matmul of the same bf16 values."""
+    T, C, HID = 64800, 768, 3072
+    mode = ops.MODE_BF16
+    f32mm = lambda a, b: a.float() @ b.float()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        if name == "fc1_gelu":
+            x, w, b = gen(T, C, seed=90, scale=0.5).bfloat16(), gen(HID, C, seed=91, scale=0.05).bfloat16(), gen(HID, seed=92)
+            g, h = ops.gemm(mode, x, 0, w, 0, EPI_BIAS_GELU, bias=b)
+            h_ref = f32mm(x, w.t()) + b
+            assert rel(h, h_ref) < 6e-3
+            assert rel(g, torch.nn.functional.gelu(h.float())) < 6e-3      # GELU of the stored pre-activation
+        elif name == "fc2":
+            x, w, b = gen(T, HID, seed=93, scale=0.5).bfloat16(), gen(C, HID, seed=94, scale=0.05).bfloat16(), gen(C, seed=95)
+            assert rel(ops.gemm(mode, x, 0, w, 0, EPI_BIAS, bias=b), f32mm(x, w.t()) + b) < 6e-3
+        elif name == "dgelu":
+            dz, w, h = gen(T, C, seed=96, scale=0.5).bfloat16(), gen(C, HID, seed=97, scale=0.05).bfloat16(), gen(T, HID, seed=98).bfloat16()
+            hf = h.float().requires_grad_(True)
+            torch.nn.functional.gelu(hf).backward(f32mm(dz, w))
+            assert rel(ops.gemm(mode, dz, 0, w, 1, EPI_DGELU, aux=h), hf.grad) < 6e-3
+        elif name == "qkv_dgrad":
+            dy, w, r = gen(T, 3 * C, seed=99, scale=0.5).bfloat16(), gen(3 * C, C, seed=100, scale=0.05).bfloat16(), gen(T, C, seed=101)
+            assert rel(ops.gemm(mode, dy, 0, w, 1, EPI_ADD_F32, aux=r), f32mm(dy, w) + r) < 1e-5
+        else:
+            dy, x = gen(T, HID, seed=102, scale=0.5).bfloat16(), gen(T, C, seed=103, scale=0.5).bfloat16()
+            dw = torch.zeros(HID, C, device=DEV)
+            ops.gemm(mode, dy, 1, x, 1, EPI_F32, out=dw, accumulate=True, split_k=ops.wgrad_split_k(HID, C, T))
+            # 64,800-term fp32 reductions: compare against fp64 on a slice of rows (the fp32 matmul reference carries
+            # the same ~eps*sqrt(K) accumulation noise as the kernel) and against fp32 overall
+            rows = torch.arange(0, HID, 48, device=DEV)
+            ref64 = dy[:, rows].double().t() @ x.double()
+            assert rel(dw[rows].double(), ref64) < 2e-5
+            assert rel(dw, f32mm(dy.t(), x)) < 5e-5
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 @pytest.mark.parametrize("split_k", [2, 5, 16])
 def test_gemm_tcgen05_split_k(split_k):
     run_gemm_case((768, 3072, 4000, 1, 1, EPI_F32), torch.bfloat16, BACKEND_TCGEN05, split_k)

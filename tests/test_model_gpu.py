@@ -196,3 +196,33 @@ def test_multistep_rollout_gradients(mode):
     tol = 1e-5 if mode == "fp32" else 1e-2
     check(pred.detach().cpu(), float(loss), grads, torch.cat([p1, p2], dim=1).detach(), loss_ref.detach(), grads_ref, tol,
           5e-5 if mode == "fp32" else 5e-2)
+
+
+def test_full_resolution_batch_independence():
+    """BASELINE size (73 channels, 720 x 1440, C = 768, 8 heads), one block: no kernel mixes samples, so sample 0 of a
+    two-sample batch must reproduce the single-sample run bit for bit in the forward (no atomics there) and to fp32
+    accumulation-order noise in the gradients; the batch loss is the sum of the per-sample losses (losses.py:200-204)."""
+    torch.manual_seed(0)
+    kw = dict(img_size=(720, 1440), patch_size=4, depths=(1,), num_heads=(8,), in_chans=73, out_chans=73, embed_dim=768,
+              img_window_ratio=80, drop_path_rate=0.0, full_pos_embed=True, rel_pos=False, mlp_ratio=4.0, residual=False)
+    model = SwinTransformerV2Cr(compute_mode="bf16", **kw).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 73, 720, 1440, generator=g).cuda()
+    t = torch.randn(2, 73, 720, 1440, generator=g).cuda()
+    qw = O.quadrature_row_weights(720, 1440).cuda()
+    chw = torch.full((73,), 1.0 / 73, device="cuda")
+
+    def run(xb, tb):
+        model.zero_grad(set_to_none=True)
+        pred = model(xb)
+        loss = LatWeightedL2Fn.apply(pred, tb, qw, chw, True, True)
+        loss.backward()
+        return pred.detach(), float(loss.detach()), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    p2, l2, g2 = run(x, t)
+    p0, l0, g0 = run(x[:1].contiguous(), t[:1].contiguous())
+    p1, l1, g1 = run(x[1:].contiguous(), t[1:].contiguous())
+    assert torch.equal(p2[:1], p0) and torch.equal(p2[1:], p1)
+    assert abs(l2 - (l0 + l1)) / abs(l2) < 1e-6
+    for k in g2:
+        assert O.rel_l2(g2[k].cpu(), (g0[k] + g1[k]).cpu()) < 2e-3, k
