@@ -780,13 +780,13 @@ extern "C" int swinb200_ln_residual_fwd(const void* z, int act_dtype, const floa
 }
 
 // ---- bf16 fast path for C = 128*NK channels (the model's C = 768) ---------------------------------------------------
-// One producer warp keeps a 3-stage ring of 8-row tiles (dx fp32 + z bf16, two cp.async.bulk per tile) in flight; each of
-// the 8 consumer warps owns one row of every tile and does the whole row from registers: lane l holds channels
+// One producer warp keeps a 3-stage ring of 10-row tiles (dx fp32 + z bf16, two cp.async.bulk per tile) in flight; each of
+// the 10 consumer warps owns one row of every tile and does the whole row from registers: lane l holds channels
 // {l*4 + 128*k + e} (conflict-free 16-byte / 8-byte shared loads), two warp reductions give the row means, dz goes to the
 // warp's own staging row and leaves with a 1.5 KB cp.async.bulk store.  No CTA-wide barrier in the loop; the ring slot is
 // released as soon as the row sits in registers.  Per-channel sums (dgamma, dbeta, bias gradient of the previous Linear)
 // stay in registers, are folded through shared memory once per CTA and reach HBM as one atomic per channel per CTA.
-constexpr int kLnbRows = 8, kLnbStages = 3, kLnbThreads = 32 * (kLnbRows + 1);
+constexpr int kLnbRows = 10, kLnbStages = 3, kLnbThreads = 32 * (kLnbRows + 1);
 __device__ __forceinline__ void lnb_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
 }
@@ -795,8 +795,9 @@ struct LnbSmem {
   static constexpr int C = 128 * NK;
   static constexpr int kDx = kLnbRows * C * 4, kZ = kLnbRows * C * 2, kStage = kDx + kZ;
   static constexpr int kOffOut = kLnbStages * kStage;                 // [warp][2][C] bf16
-  static constexpr int kOffRed = kOffOut + kLnbRows * 2 * C * 2;      // [3][C] fp32
-  static constexpr int kOffBar = kOffRed + 3 * C * 4;
+  static constexpr int kOffRed = kOffOut + kLnbRows * 2 * C * 2;      // [3][C] fp32 sums
+  static constexpr int kOffGamma = kOffRed + 3 * C * 4;               // [C] gamma
+  static constexpr int kOffBar = kOffGamma + C * 4;
   static constexpr int kBytes = kOffBar + 64;
 };
 
@@ -823,6 +824,8 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 3 * C; i += kLnbThreads) red[i] = 0.f;
+  float* sgamma = reinterpret_cast<float*>(lsm + SM::kOffGamma);      // read per row from smem: 24 registers per lane stay free
+  for (int i = tid; i < C; i += kLnbThreads) sgamma[i] = __ldg(gamma + i);
   __syncthreads();
 
   if (warp == kLnbRows) {
@@ -842,14 +845,12 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
     }
   } else {
     // ------------------------------------------------ consumers: warp w <-> row w of every tile ----------------------
-    float gm[NK][4], a_g[NK][4], a_b[NK][4], a_z[NK][4];
+    float a_g[NK][4], a_b[NK][4], a_z[NK][4];
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * k));
-      gm[k][0] = g4.x; gm[k][1] = g4.y; gm[k][2] = g4.z; gm[k][3] = g4.w;
+    for (int k = 0; k < NK; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) { a_g[k][e] = 0.f; a_b[k][e] = 0.f; a_z[k][e] = 0.f; }
-    }
+    const float4* gm4 = reinterpret_cast<const float4*>(sgamma);
     unsigned char* obuf = lsm + SM::kOffOut + warp * 2 * C * 2;
     const float invC = 1.0f / (float)C;
     int it = 0, nstores = 0;
@@ -864,7 +865,8 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
         if (sample_scale) sc = __ldg(sample_scale + row / rows_per_sample);
       }
       lnb_mbar_wait(&full[stage], (uint32_t)((it / kLnbStages) & 1));
-      float d[NK][4], zv[NK][4];
+      float d[NK][4];
+      uint2 zp[NK];                                  // z stays packed (4 x bf16) until it is used
       if (active) {
         const unsigned char* st = lsm + stage * SM::kStage;
         const float4* dxr = reinterpret_cast<const float4*>(st + (size_t)warp * C * 4);
@@ -872,10 +874,8 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
           const float4 d4 = dxr[lane + 32 * k];
-          const uint2 z2 = zr[lane + 32 * k];
+          zp[k] = zr[lane + 32 * k];
           d[k][0] = d4.x; d[k][1] = d4.y; d[k][2] = d4.z; d[k][3] = d4.w;
-          zv[k][0] = __uint_as_float(z2.x << 16); zv[k][1] = __uint_as_float(z2.x & 0xffff0000u);
-          zv[k][2] = __uint_as_float(z2.y << 16); zv[k][3] = __uint_as_float(z2.y & 0xffff0000u);
         }
       }
       // the row is in registers: the slot may be refilled.  The refill is an async-proxy write after these generic-proxy
@@ -886,13 +886,18 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
       if (!active) continue;
       float A = 0.f, Bq = 0.f;
 #pragma unroll
-      for (int k = 0; k < NK; ++k)
+      for (int k = 0; k < NK; ++k) {
+        const float4 g4 = gm4[lane + 32 * k];
+        const float gmk[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float zk[4] = {__uint_as_float(zp[k].x << 16), __uint_as_float(zp[k].x & 0xffff0000u),
+                             __uint_as_float(zp[k].y << 16), __uint_as_float(zp[k].y & 0xffff0000u)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float g = d[k][e] * gm[k][e];
+          const float g = d[k][e] * gmk[e];
           A += g;
-          Bq = fmaf(g, zv[k][e], Bq);
+          Bq = fmaf(g, zk[e], Bq);
         }
+      }
       A = warp_sum(A);
       Bq = warp_sum(Bq);
       const float xo = -mean * rstd;                          // xhat = z * rstd + xo
@@ -904,11 +909,15 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
         float o4[4];
+        const float4 g4 = gm4[lane + 32 * k];
+        const float gmk[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float zk[4] = {__uint_as_float(zp[k].x << 16), __uint_as_float(zp[k].x & 0xffff0000u),
+                             __uint_as_float(zp[k].y << 16), __uint_as_float(zp[k].y & 0xffff0000u)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float du = d[k][e] * sc;
-          const float xh = fmaf(zv[k][e], rstd, xo);
-          o4[e] = rstd * (fmaf(du, gm[k][e], -mg) - xh * mgx);
+          const float xh = fmaf(zk[e], rstd, xo);
+          o4[e] = rstd * (fmaf(du, gmk[e], -mg) - xh * mgx);
           a_b[k][e] += du;
           a_g[k][e] = fmaf(du, xh, a_g[k][e]);
           a_z[k][e] += o4[e];
