@@ -307,6 +307,57 @@ def run_ours(args):
     families = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps}
                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
 
+    # ---- optimizer step, reported separately ("optimizer step reported separately"; 8(f) rank 1) ----------
+    optimizer = None
+    if world == 1:
+        from swin_v2_weather_b200.functional import SHADOWS
+        from swin_v2_weather_b200.optim import Adam
+        inner = model.module if hasattr(model, "module") else model
+        prm = [p for p in inner.parameters() if p.grad is not None]
+        n_elem = sum(p.numel() for p in prm)
+        n_shadow = sum(p.numel() for p in prm if SHADOWS.peek(p) is not None)
+
+        def time_steps(opt, n=5):
+            for _ in range(2):
+                opt.step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                opt.step()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        # lr = 0 keeps the benchmark weights unchanged while moving exactly the same bytes
+        ours_ms = time_steps(Adam(prm, lr=0.0, betas=(0.9, 0.95)))
+        torch_opt = torch.optim.Adam(prm, lr=0.0, betas=(0.9, 0.95), fused=True)
+        torch_ms = time_steps(torch_opt)
+        del torch_opt
+
+        def recast():
+            for p in prm:
+                sh = SHADOWS.peek(p)
+                if sh is not None:
+                    from swin_v2_weather_b200 import ops as _ops
+                    _ops.cast_bf16(p.detach(), sh)
+        recast()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            recast()
+        e1.record()
+        torch.cuda.synchronize()
+        recast_ms = e0.elapsed_time(e1) / 5
+        alg_bytes = n_elem * 28 + n_shadow * 2
+        optimizer = {"kernel": "adam_multi_kernel (fp32 masters + moments + bf16 shadows in one pass)", "ms": round(ours_ms, 3),
+                     "bound": "hbm", "achieved_gbs": round(alg_bytes / ours_ms / 1e6, 1), "peak_gbs": peaks["hbm"],
+                     "frac": round(alg_bytes / ours_ms / 1e6 / peaks["hbm"], 4), "algorithmic_bytes": alg_bytes,
+                     "torch_fused_adam_ms": round(torch_ms, 3), "separate_shadow_recast_ms": round(recast_ms, 3),
+                     "parameters": n_elem, "parameters_with_bf16_shadow": n_shadow,
+                     "note": "not part of `value` (the metric is fwd+bwd); lr=0 so the timed weights do not move"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_samples_per_s(budget_s=60.0)
@@ -327,6 +378,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roof,
         "kernel_families": families,
+        "optimizer_step": optimizer,
         "model_tflops": round(value * FLOPS_FWD_BWD / 1e12 / world, 1),
         "model_frac_of_sustained_peak": round(value * FLOPS_FWD_BWD / 1e12 / world / peaks["tf_sust"], 4),
         "peak_mem_gib": round(peak_mem, 2),

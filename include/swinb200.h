@@ -143,6 +143,19 @@ int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, co
                          const float* num, const float* den, const float* gloss, int relative, int squared,
                          float* dprd, int B, int C, int H, int W, void* stream);
 
+/* ---- optimizer ------------------------------------------------------------------
+ * One fused multi-tensor pass of torch.optim.Adam(lr, betas, eps, weight_decay, amsgrad=False) as the reference
+ * configures it (train.py:175-176), over n_tensors fp32 parameters given as HOST arrays of DEVICE pointers:
+ *   g = grad / *grad_scale (+ weight_decay * p);  m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)
+ * and, where shadows[i] != NULL, the bf16 copy of the new p that the tensor-core GEMMs read (replaces the per-step
+ * swinb200_cast_f32_to_bf16 pass).  grad_scale / found_inf: optional device scalars with torch.amp.GradScaler's meaning
+ * (train.py:281-289); a non-zero *found_inf skips the whole step on the device.  step counts from 1. */
+int swinb200_adam_step(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                       void* const* exp_avg_sq, void* const* shadows, const long long* numel, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, long long step,
+                       const float* grad_scale, const float* found_inf, void* stream);
+
 /* ---- bring-up / test hook ------------------------------------------------------------------------------
  * D[128,N] (fp32) = A[128,K] * B[N,K]^T through one tcgen05.mma chain using the un-swizzled core-matrix
  * shared-memory layout of the attention kernels.  a_mode: 0 = A (128,K) from smem K-major, 1 = A stored (K,128)

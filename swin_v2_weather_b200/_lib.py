@@ -38,6 +38,8 @@ PROTOTYPES = {
     "swinb200_debug_attn_phase_buffer": [_P],
     "swinb200_debug_umma_probe": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "swinb200_latw_l2_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P],
+    "swinb200_adam_step": [_I, _P, _P, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                           ctypes.c_double, ctypes.c_longlong, _P, _P, _P],
 }
 
 _lib = None

@@ -40,6 +40,19 @@ class _ShadowCache:
         self._store[key] = (weakref.ref(w), ver, ptr, sh)
         return sh
 
+    def peek(self, w: torch.Tensor):
+        """The live shadow of `w` (possibly stale), or None -- lets the fused optimizer rewrite it in its own pass."""
+        ent = self._store.get(id(w))
+        if ent is not None and ent[0]() is w and ent[2] == w.data_ptr() and ent[3].shape == w.shape:
+            return ent[3]
+        return None
+
+    def mark_fresh(self, w: torch.Tensor) -> None:
+        """The shadow of `w` has just been rewritten from its current value by someone else (optim.Adam)."""
+        ent = self._store.get(id(w))
+        if ent is not None and ent[0]() is w:
+            self._store[id(w)] = (ent[0], w._version, w.data_ptr(), ent[3])
+
     def clear(self):
         self._store.clear()
 

@@ -517,3 +517,77 @@ def test_gemm_tcgen05_persistent_many_tiles():
     # more tiles than SMs: exercises the TMEM double buffering and the smem ring wrap-around
     run_gemm_case((128 * 40, 2304, 768, 0, 0, EPI_BIAS), torch.bfloat16, BACKEND_TCGEN05)
     run_gemm_case((128 * 40 + 17, 3072, 768, 0, 0, EPI_BIAS_GELU), torch.bfloat16, BACKEND_TCGEN05)
+
+
+# ---- optimizer --------------------------------------------------------------------------
+@pytest.mark.parametrize("weight_decay", [0.0, 0.01])
+def test_adam_matches_torch_fused(weight_decay):
+    """swin_v2_weather_b200.optim.Adam vs torch.optim.Adam(fused=True) as the reference builds it (betas 0.9 / 0.95):
+    ten steps on tensors of awkward sizes (chunk tails, one-element, 3 M elements), fp32 tolerance."""
+    from swin_v2_weather_b200.optim import Adam
+    shapes = [(1,), (7,), (768,), (2304, 768), (65536 + 3,), (3, 1000, 1000), (5, 13)]
+    torch.manual_seed(0)
+    ref_p = [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=3e-3, betas=(0.9, 0.95), weight_decay=weight_decay, fused=True)
+    ours = Adam(our_p, lr=3e-3, betas=(0.9, 0.95), weight_decay=weight_decay, fused=True)
+    for it in range(10):
+        for a, b in zip(ref_p, our_p):
+            g = torch.randn_like(a) * (10.0 ** (it % 3 - 1))
+            a.grad, b.grad = g, g.clone()
+        ref.step()
+        ours.step()
+    for a, b in zip(ref_p, our_p):
+        assert rel(b, a) < 2e-6
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    assert sd_ref["state"].keys() == sd_ours["state"].keys()
+    for k in sd_ref["state"]:
+        assert set(sd_ref["state"][k]) == set(sd_ours["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sd_ref["state"][k]["step"]) == float(sd_ours["state"][k]["step"]) == 10
+        assert rel(sd_ours["state"][k]["exp_avg"], sd_ref["state"][k]["exp_avg"]) < 2e-6
+        assert rel(sd_ours["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"]) < 2e-6
+    # a torch Adam state_dict loads into ours and training continues identically
+    ours2 = Adam([torch.nn.Parameter(p.detach().clone()) for p in ref_p], lr=3e-3, betas=(0.9, 0.95), weight_decay=weight_decay)
+    import copy
+    ours2.load_state_dict(copy.deepcopy(sd_ref))      # (load_state_dict aliases same-device tensors of the dict it is given)
+    for a, b in zip(ref_p, ours2.param_groups[0]["params"]):
+        g = torch.randn_like(a)
+        a.grad, b.grad = g, g.clone()
+    ref.step()
+    ours2.step()
+    for a, b in zip(ref_p, ours2.param_groups[0]["params"]):
+        assert rel(b, a) < 2e-6
+
+
+def test_adam_refreshes_bf16_shadows_and_honours_grad_scaler():
+    from swin_v2_weather_b200.functional import SHADOWS
+    from swin_v2_weather_b200.optim import Adam
+    w = torch.nn.Parameter(gen(300, 96, seed=120))
+    sh0 = SHADOWS.get(w, ops.MODE_BF16)
+    assert torch.equal(sh0.float(), w.detach().bfloat16().float())
+    opt = Adam([w], lr=1e-2, betas=(0.9, 0.95))
+    w.grad = gen(300, 96, seed=121) * 1024.0                   # scaled gradient, GradScaler style
+    opt.grad_scale = torch.tensor(1024.0, device=DEV)
+    opt.found_inf = torch.tensor(0.0, device=DEV)
+    before, v0 = w.detach().clone(), w._version
+    opt.step()
+    assert w._version > v0                                      # autograd sees the in-place update
+    sh1 = SHADOWS.get(w, ops.MODE_BF16)
+    assert sh1.data_ptr() == sh0.data_ptr()                     # same buffer, rewritten by the optimizer pass (no re-cast)
+    assert torch.equal(sh1.float(), w.detach().bfloat16().float())
+    ref = torch.nn.Parameter(before.clone())
+    ropt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.95), fused=True)
+    ref.grad = gen(300, 96, seed=121)
+    ropt.step()
+    assert rel(w, ref) < 2e-6
+    # overflow: the step is skipped on the device
+    opt.found_inf = torch.tensor(1.0, device=DEV)
+    snap = w.detach().clone()
+    opt.step()
+    assert torch.equal(w.detach(), snap)
+    scaler = torch.amp.GradScaler("cuda", init_scale=256.0)
+    loss = (w * gen(300, 96, seed=122)).sum()
+    scaler.scale(loss).backward()
+    scaler.step(opt)                                            # takes the _step_supports_amp_scaling path
+    scaler.update()
+    assert not torch.equal(w.detach(), snap)

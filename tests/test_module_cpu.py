@@ -91,6 +91,21 @@ def test_no_cpu_fallback():
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
 
 
+def test_optimizer_mirrors_torch_adam_surface_and_has_no_cpu_fallback():
+    from swin_v2_weather_b200._lib import SwinB200Error
+    from swin_v2_weather_b200.optim import Adam
+    w = torch.nn.Parameter(torch.randn(4, 3))
+    opt = Adam([w], lr=1e-3, betas=(0.9, 0.95), fused=True)              # the reference's call (train.py:175-176)
+    ref = torch.optim.Adam([torch.nn.Parameter(w.detach().clone())], lr=1e-3, betas=(0.9, 0.95))
+    assert set(ref.state_dict()["param_groups"][0]) <= set(opt.state_dict()["param_groups"][0])
+    assert opt._step_supports_amp_scaling
+    w.grad = torch.randn(4, 3)
+    with pytest.raises(SwinB200Error, match="CUDA"):
+        opt.step()
+    with pytest.raises(NotImplementedError):
+        Adam([w], amsgrad=True)
+
+
 def test_wrong_image_size_raises_like_reference():
     m = small()
     with pytest.raises(AssertionError, match="doesn't match model"):
