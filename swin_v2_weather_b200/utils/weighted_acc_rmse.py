@@ -1,0 +1,44 @@
+"""Latitude-weighted RMSE of the validation loop (reference utils/weighted_acc_rmse.py:51-87, train.py:305-351), SURVEY 8(f)
+rank 4: the same bandwidth-bound weighted reduction as the training loss, so it runs on the loss kernel
+(`swinb200_latw_l2_fwd`: num[b, c] = sum_hw qw[h] (p - t)^2) with the reference's own row weights
+
+    w[h] = num_lat * cos(3.1416/180 * lat(h)) / sum_h cos(3.1416/180 * lat(h)),   lat(h) = 90 - h * 180/(num_lat - 1)
+
+(the reference really uses 3.1416, `:56`) folded with the 1/(H W) of its `torch.mean`.  One pass over pred and target
+instead of the reference's four elementwise passes + reduction.  CUDA tensors only (no CPU fallback).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+def lat(j: torch.Tensor, num_lat: int) -> torch.Tensor:
+    return 90. - j * 180. / float(num_lat - 1)
+
+
+def latitude_weighting_factor_torch(j: torch.Tensor, num_lat: int, s: torch.Tensor) -> torch.Tensor:
+    return num_lat * torch.cos(3.1416 / 180. * lat(j, num_lat)) / s
+
+
+def _row_weights(num_lat: int, num_lon: int, device) -> torch.Tensor:
+    lat_t = torch.arange(start=0, end=num_lat, device=device)
+    s = torch.sum(torch.cos(3.1416 / 180. * lat(lat_t, num_lat)))
+    w = latitude_weighting_factor_torch(lat_t, num_lat, s)
+    return (w / float(num_lat * num_lon)).to(torch.float32).contiguous()
+
+
+def weighted_rmse_torch_channels(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """(n, c, h, w) x 2 -> latitude-weighted RMSE per sample and channel, (n, c)."""
+    if pred.shape != target.shape or pred.dim() != 4:
+        raise ValueError(f"weighted_rmse: expected two (n, c, h, w) tensors, got {tuple(pred.shape)} and {tuple(target.shape)}")
+    n, c, h, w = pred.shape
+    qw = _row_weights(h, w, pred.device)
+    ones = torch.ones((c,), dtype=torch.float32, device=pred.device)
+    _, num, _ = ops.latw_l2_fwd(pred.detach().float().contiguous(), target.detach().float().contiguous(), qw, ones, False, True)
+    return torch.sqrt(num.view(n, c))
+
+
+def weighted_rmse_torch(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    return torch.mean(weighted_rmse_torch_channels(pred, target), dim=0)

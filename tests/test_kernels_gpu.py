@@ -591,3 +591,17 @@ def test_adam_refreshes_bf16_shadows_and_honours_grad_scaler():
     scaler.step(opt)                                            # takes the _step_supports_amp_scaling path
     scaler.update()
     assert not torch.equal(w.detach(), snap)
+
+
+def test_validation_weighted_rmse_matches_reference_formula():
+    """utils/weighted_acc_rmse.py:59-87 restated with plain torch ops (the oracle here) vs the kernel-backed version."""
+    from swin_v2_weather_b200.utils.weighted_acc_rmse import weighted_rmse_torch, weighted_rmse_torch_channels
+    n, c, h, w = 2, 5, 72, 144
+    pred, tar = gen(n, c, h, w, seed=130), gen(n, c, h, w, seed=131)
+    lat_t = torch.arange(0, h, device=DEV)
+    latv = 90. - lat_t * 180. / float(h - 1)
+    s = torch.sum(torch.cos(3.1416 / 180. * latv))
+    weight = (h * torch.cos(3.1416 / 180. * latv) / s).reshape(1, 1, -1, 1)
+    want = torch.sqrt(torch.mean(weight * (pred - tar) ** 2., dim=(-1, -2)))
+    assert rel(weighted_rmse_torch_channels(pred, tar), want) < 1e-6
+    assert rel(weighted_rmse_torch(pred, tar), want.mean(0)) < 1e-6
