@@ -61,6 +61,13 @@ int swinb200_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* strea
  *            networks/helpers.py:26-41). */
 int swinb200_patchify(const float* img, void* out, int act_dtype, int B, int C, int Hi, int Wi, int P,
                       int order, void* stream);
+/* swinb200_patchify_cat: order-0 im2col whose image channels come from n_src (<= 8) separate (B or 1, chans[s], Hi, Wi)
+ *   fp32 tensors (HOST arrays of DEVICE pointers / channel counts / per-sample strides in elements, 0 = shared by the
+ *   batch).  Replaces torch.cat([inp, zenith, static_features], dim=1) of PreProcessor.forward
+ *   (utils/preprocess_utils.py:50-68) and of the MultiStepWrapper rollout (networks/helpers.py:36-40) followed by
+ *   PatchEmbed's im2col: the concatenated image is never materialised. */
+int swinb200_patchify_cat(int n_src, const float* const* srcs, const int* chans, const long long* batch_strides,
+                          void* out, int act_dtype, int B, int Hi, int Wi, int P, void* stream);
 int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out,
                         int B, int Co, int Hi, int Wi, int P, int order, void* stream);
 

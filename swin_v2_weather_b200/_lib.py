@@ -23,6 +23,7 @@ _I = c_int
 PROTOTYPES = {
     "swinb200_cast_f32_to_bf16": [_P, _P, c_size_t, _P],
     "swinb200_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "swinb200_patchify_cat": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "swinb200_unpatchify": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "swinb200_gemm": [_I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "swinb200_ln_residual_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, c_float, _P],

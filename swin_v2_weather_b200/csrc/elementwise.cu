@@ -134,6 +134,52 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 
 // y (T, P*P*Co) -> out (B, Co, Hi, Wi) (+ skip[:, :Co]); ORDER 1: columns (p, q, c) (output head), ORDER 0: (c, p, q)
 // (gradient of the PatchEmbed im2col, i.e. dL/d image for multi-step rollouts)
+// Same im2col (order 0) reading the image channels from up to 8 separate tensors -- the field, the zenith-angle channel
+// and the static land-mask / orography features (utils/preprocess_utils.py:50-68, networks/helpers.py:36-40) -- so the
+// concatenated (B, 77, 720, 1440) input is never written: a source with batch stride 0 is shared by every sample.
+constexpr int kPatchMaxSrc = 8;
+struct PatchSrcs {
+  const float* ptr[kPatchMaxSrc];
+  long long bstride[kPatchMaxSrc];   // elements between samples (0: broadcast over the batch)
+  int c0[kPatchMaxSrc + 1];          // first concatenated-channel index of each source; c0[n] = C
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_cat_kernel(const __grid_constant__ PatchSrcs src, T* __restrict__ out, int B, int C,
+                                                           int Hi, int Wi, int ntok) {
+  constexpr int P = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int K = C * P * P;
+  const int pitch = K + 8;
+  const int H = Hi / P, W = Wi / P;
+  const int t0 = blockIdx.x * kPatchTok;
+  const int ntile = min(kPatchTok, ntok - t0);
+  const int items = C * P * kPatchTok;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int tok = it % kPatchTok;
+    const int cp = it / kPatchTok;
+    const int p = cp % P, c = cp / P;
+    if (tok >= ntile) continue;
+    int s = 0;
+    while (s + 1 < src.n && c >= src.c0[s + 1]) ++s;
+    const int t = t0 + tok;
+    const int j = t % W, i = (t / W) % H, b = t / (W * H);
+    const float* base = src.ptr[s] + (size_t)b * src.bstride[s] + ((size_t)(c - src.c0[s]) * Hi + (i * P + p)) * Wi + j * P;
+    const float4 v = *reinterpret_cast<const float4*>(base);
+    T* d = tile + (size_t)tok * pitch + (c * P + p) * P;
+    Act<T>::st(d + 0, v.x); Act<T>::st(d + 1, v.y); Act<T>::st(d + 2, v.z); Act<T>::st(d + 3, v.w);
+  }
+  __syncthreads();
+  const int k8 = K / 8;
+  for (int it = threadIdx.x; it < ntile * k8; it += blockDim.x) {
+    const int tok = it / k8, kc = it % k8;
+    float v[8];
+    ld8(tile + (size_t)tok * pitch + kc * 8, v);
+    st8(out + (size_t)(t0 + tok) * K + kc * 8, v);
+  }
+}
+
 template <typename T, int ORDER>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y, const float* __restrict__ skip,
                                                          int skip_chans, float* __restrict__ out, int B, int Co, int Hi,
@@ -715,6 +761,39 @@ extern "C" int swinb200_patchify(const float* img, void* out, int act_dtype, int
   if (act_dtype == SWINB200_BF16) return launch_patchify<__nv_bfloat16>(img, (__nv_bfloat16*)out, B, C, Hi, Wi, order, (cudaStream_t)stream);
   if (act_dtype == SWINB200_F32) return launch_patchify<float>(img, (float*)out, B, C, Hi, Wi, order, (cudaStream_t)stream);
   SWB_CHECK_ARG(false, "patchify: bad act_dtype %d", act_dtype);
+}
+
+extern "C" int swinb200_patchify_cat(int n_src, const float* const* srcs, const int* chans, const long long* batch_strides, void* out,
+                                     int act_dtype, int B, int Hi, int Wi, int P, void* stream) {
+  SWB_CHECK_ARG(n_src >= 1 && n_src <= kPatchMaxSrc && srcs && chans && batch_strides && out, "patchify_cat: 1..%d sources", kPatchMaxSrc);
+  SWB_CHECK_ARG(P == 4, "patchify_cat: only patch_size 4 is supported (got %d)", P);
+  SWB_CHECK_ARG(B > 0 && Hi % 4 == 0 && Wi % 4 == 0, "patchify_cat: bad shape B=%d Hi=%d Wi=%d", B, Hi, Wi);
+  PatchSrcs ps;
+  int C = 0;
+  for (int s = 0; s < n_src; ++s) {
+    SWB_CHECK_ARG(srcs[s] && chans[s] > 0 && batch_strides[s] >= 0 && ((uintptr_t)srcs[s] % 16 == 0) && batch_strides[s] % 4 == 0,
+                  "patchify_cat: source %d is null, empty or not 16-byte aligned", s);
+    ps.ptr[s] = srcs[s]; ps.bstride[s] = batch_strides[s]; ps.c0[s] = C;
+    C += chans[s];
+  }
+  ps.c0[n_src] = C;
+  ps.n = n_src;
+  SWB_CHECK_ARG((size_t)kPatchTok * (C * 16 + 8) * 4 <= 220 * 1024, "patchify_cat: C=%d too large", C);
+  const int ntok = B * (Hi / 4) * (Wi / 4);
+  const int blocks = (ntok + kPatchTok - 1) / kPatchTok;
+  if (act_dtype == SWINB200_BF16) {
+    const size_t smem = (size_t)kPatchTok * (C * 16 + 8) * 2;
+    SWB_CUDA(cudaFuncSetAttribute(patchify_cat_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patchify_cat_kernel<__nv_bfloat16><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, (__nv_bfloat16*)out, B, C, Hi, Wi, ntok);
+  } else if (act_dtype == SWINB200_F32) {
+    const size_t smem = (size_t)kPatchTok * (C * 16 + 8) * 4;
+    SWB_CUDA(cudaFuncSetAttribute(patchify_cat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    patchify_cat_kernel<float><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, (float*)out, B, C, Hi, Wi, ntok);
+  } else {
+    SWB_CHECK_ARG(false, "patchify_cat: bad act_dtype %d", act_dtype);
+  }
+  SWB_LAUNCH_CHECK();
+  return SWINB200_OK;
 }
 
 template <typename T>

@@ -70,20 +70,28 @@ class PatchEmbedFn(torch.autograd.Function):
     Returns the fp32 token stream (B, H, W, C) and its activation-type shadow."""
 
     @staticmethod
-    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode):
+    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode, *more_channels):
+        """`more_channels`: further (B or 1, C_s, Hi, Wi) tensors whose channels follow those of `img` (zenith angle, static
+        land-mask / orography features): the im2col reads all of them in place, torch.cat never runs."""
         ctx.set_materialize_grads(False)   # no zero-filled gradient for the (non-differentiable) bf16 shadow output
-        B, Cin, Hi, Wi = img.shape
+        B, C0, Hi, Wi = img.shape
+        Cin = C0 + sum(t.shape[1] for t in more_channels)
         E = proj_w.shape[0]
         H, W = Hi // patch, Wi // patch
-        patches = ops.patchify(img.contiguous(), patch, 0, mode)                       # (T, Cin*P*P)
+        if more_channels:
+            patches = ops.patchify_cat([img.contiguous()] + [t.detach().float().contiguous() for t in more_channels], patch, mode)
+        else:
+            patches = ops.patchify(img.contiguous(), patch, 0, mode)                   # (T, Cin*P*P)
         w2 = SHADOWS.get(proj_w, mode).reshape(E, -1)
+        if w2.shape[1] != patches.shape[1]:
+            raise ValueError(f"PatchEmbed: input has {Cin} channels, the projection expects {w2.shape[1] // (patch * patch)}")
         z0 = ops.gemm(mode, patches, 0, w2, 0, EPI_BIAS, bias=proj_b.detach())        # (T, E)
         pos_tok = None
         if pos_embed is not None:
             pos_tok = ops.transpose_f32(pos_embed.detach().reshape(E, H * W))          # (H*W, E) token-major
         x, xb, stats = ops.ln_residual_fwd(z0, None, norm_w.detach(), norm_b.detach(), None, pos_tok, H * W, mode)
         ctx.save_for_backward(patches, z0, stats, norm_w, proj_w)
-        ctx.meta = (B, Cin, Hi, Wi, E, H, W, patch, mode, pos_embed is not None, tuple(proj_w.shape))
+        ctx.meta = (B, C0, Cin, Hi, Wi, E, H, W, patch, mode, pos_embed is not None, tuple(proj_w.shape), len(more_channels))
         shadow = xb if mode.act_dtype != torch.float32 else x.new_empty(0)   # fp32 mode: the stream is its own shadow
         ctx.mark_non_differentiable(shadow)
         return x.view(B, H, W, E), shadow
@@ -91,7 +99,7 @@ class PatchEmbedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx, _dxb):
         patches, z0, stats, norm_w, proj_w = ctx.saved_tensors
-        B, Cin, Hi, Wi, E, H, W, patch, mode, has_pos, wshape = ctx.meta
+        B, C0, Cin, Hi, Wi, E, H, W, patch, mode, has_pos, wshape, n_more = ctx.meta
         dx = dx.contiguous().view(B * H * W, E)
         dpos = ops.pos_embed_grad(dx, B, H * W, E).view(1, E, H, W) if has_pos else None
         dz0, dgamma, dbeta, dbias = ops.ln_residual_bwd(dx, z0, stats, norm_w.detach(), None, H * W, mode)
@@ -101,11 +109,14 @@ class PatchEmbedFn(torch.autograd.Function):
         dimg = None
         if ctx.needs_input_grad[0]:
             # multi-step rollouts (networks/helpers.py:26-41) back-propagate into the previous step's prediction:
-            # d patches = dz0 @ W (dgrad GEMM, weight read n-major), scattered back by the im2col adjoint
+            # d patches = dz0 @ W (dgrad GEMM, weight read n-major), scattered back by the im2col adjoint.  Only the
+            # channels of `img` itself carry a gradient (the appended zenith / static channels are data).
             w2 = SHADOWS.get(proj_w, mode).reshape(E, -1)
-            dpatch = ops.gemm(mode, dz0, 0, w2, 1, EPI_BIAS)                          # (T, Cin*P*P), columns (c, p, q)
-            dimg = ops.unpatchify(dpatch, None, B, Cin, Hi, Wi, patch, order=0)
-        return dimg, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None
+            if C0 != Cin:
+                w2 = w2[:, :C0 * patch * patch].contiguous()
+            dpatch = ops.gemm(mode, dz0, 0, w2, 1, EPI_BIAS)                          # (T, C0*P*P), columns (c, p, q)
+            dimg = ops.unpatchify(dpatch, None, B, C0, Hi, Wi, patch, order=0)
+        return (dimg, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None) + (None,) * n_more
 
 
 # ---- one SwinV2 block ------------------------------------------------------------------------------------

@@ -26,19 +26,28 @@ class MultiStepWrapper(nn.Module):
         self.invar = 1 * params.add_orography + 2 * params.add_landmask
 
     def forward(self, inp, coszen=None):
+        """`inp` may be a tensor (as in the reference) or a tuple of channel groups from the fused PreProcessor.  The
+        re-appended zenith / invariant channels are handed to the model as separate groups: the reference's two
+        torch.cat per rollout step (2 x 319 MB written and re-read at 77 x 720 x 1440) never happen."""
         result = []
         inpt = inp
-        invars = inp[:, -self.invar:, :, :] if self.invar else None
+        if isinstance(inp, (tuple, list)):
+            flat = None if (self.invar == 0 or inp[-1].shape[1] == self.invar) else torch.cat(
+                [t.expand(inp[0].shape[0], -1, -1, -1) for t in inp], dim=1)
+            invars = None if not self.invar else (inp[-1] if flat is None else flat[:, -self.invar:, :, :].contiguous())
+        else:
+            invars = inp[:, -self.invar:, :, :].contiguous() if self.invar else None
         for step in range(self.n_future + 1):
             pred = self.model(inpt)
             result.append(pred)
             if step == self.n_future:
                 break
-            inpt = pred
+            groups = [pred]
             if coszen is not None:
-                inpt = torch.cat([inpt, coszen[:, step:step + 1, :, :]], dim=1)
+                groups.append(coszen[:, step:step + 1, :, :].contiguous())
             if self.invar:
-                inpt = torch.cat([inpt, invars], dim=1)
+                groups.append(invars)
+            inpt = groups if len(groups) > 1 else pred
         return torch.cat(result, dim=1)
 
 

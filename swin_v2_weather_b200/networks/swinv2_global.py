@@ -430,14 +430,17 @@ class SwinTransformerV2Cr(nn.Module):
         return self
 
     # -- forward ------------------------------------------------------------------------------------------
-    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_features(self, x) -> torch.Tensor:
+        """x: (B, Cin, H, W), or a tuple / list of channel groups [(B, C0, H, W), (B or 1, C1, H, W), ...] standing for their
+        concatenation along dim 1 (what PreProcessor / MultiStepWrapper would otherwise build with torch.cat)."""
         mode = ops.MODES[self.compute_mode]
-        B, C, H, W = x.shape
+        parts = [t.float() for t in x] if isinstance(x, (tuple, list)) else [x.float()]
+        B, _, H, W = parts[0].shape
         assert H == self.img_size[0], f"Input image height ({H}) doesn't match model ({self.img_size[0]})."
         assert W == self.img_size[1], f"Input image width ({W}) doesn't match model ({self.img_size[1]})."
         pe = self.patch_embed
-        tok, shadow = Fn.PatchEmbedFn.apply(x.float(), pe.proj.weight, pe.proj.bias, pe.norm.weight, pe.norm.bias,
-                                            self.pos_embed if self.full_pos_embed else None, self.patch_size, mode)
+        tok, shadow = Fn.PatchEmbedFn.apply(parts[0], pe.proj.weight, pe.proj.bias, pe.norm.weight, pe.norm.bias,
+                                            self.pos_embed if self.full_pos_embed else None, self.patch_size, mode, *parts[1:])
         x = _carry_shadow(bhwc_to_bchw(tok), shadow)
         return self.stages(x)
 
@@ -450,9 +453,15 @@ class SwinTransformerV2Cr(nn.Module):
         t = _carry_shadow(t.float(), shadow)
         return Fn.HeadFn.apply(t, _shadow_of(t, mode), self.head.weight, skip, self.out_chans, self.patch_size, mode)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = x.float()
-        skip = x if self.residual else None   # the reference adds zeros_like(x) otherwise (:795-802); adding 0 is skipped
+    def forward(self, x) -> torch.Tensor:
+        if isinstance(x, (tuple, list)):
+            x = [t.float() for t in x]
+            if self.residual and x[0].shape[1] < self.out_chans:      # the skip needs the first out_chans channels in one tensor
+                x = torch.cat([t.expand(x[0].shape[0], -1, -1, -1) for t in x], dim=1)
+        else:
+            x = x.float()
+        first = x[0] if isinstance(x, list) else x
+        skip = first if self.residual else None   # the reference adds zeros_like(x) otherwise (:795-802); adding 0 is skipped
         feats = self.forward_features(x)
         return self.forward_head(feats, skip)
 

@@ -90,6 +90,27 @@ def patchify(img: torch.Tensor, patch: int, order: int, mode: ComputeMode) -> to
     return out
 
 
+def patchify_cat(parts, patch: int, mode: ComputeMode) -> torch.Tensor:
+    """Order-0 im2col of the channel-wise concatenation of `parts` without materialising it.  Every part is a contiguous
+    fp32 (B or 1, C_s, Hi, Wi) CUDA tensor; a leading dimension of 1 is shared by the whole batch (static features)."""
+    import ctypes
+    B = max(p.shape[0] for p in parts)
+    Hi, Wi = parts[0].shape[-2:]
+    ptrs, chans, strides = [], [], []
+    for i, p in enumerate(parts):
+        if p.dim() != 4 or tuple(p.shape[-2:]) != (Hi, Wi) or p.shape[0] not in (1, B):
+            raise SwinB200Error(f"patchify_cat: part {i} has shape {tuple(p.shape)}, expected ({B} or 1, C, {Hi}, {Wi})")
+        ptrs.append(_chk(p, f"part {i}", torch.float32))
+        chans.append(p.shape[1])
+        strides.append(0 if (p.shape[0] == 1 and B > 1) else p.shape[1] * Hi * Wi)
+    n, C = len(parts), sum(chans)
+    T = B * (Hi // patch) * (Wi // patch)
+    out = torch.empty((T, C * patch * patch), dtype=mode.act_dtype, device=parts[0].device)
+    _lib.call("swinb200_patchify_cat", n, (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int * n)(*chans), (ctypes.c_longlong * n)(*strides),
+              out.data_ptr(), mode.act_code, B, Hi, Wi, patch, _stream())
+    return out
+
+
 def unpatchify(y: torch.Tensor, skip: Optional[torch.Tensor], B: int, Co: int, Hi: int, Wi: int, patch: int,
                order: int = 1) -> torch.Tensor:
     out = torch.empty((B, Co, Hi, Wi), dtype=torch.float32, device=y.device)

@@ -605,3 +605,13 @@ def test_validation_weighted_rmse_matches_reference_formula():
     want = torch.sqrt(torch.mean(weight * (pred - tar) ** 2., dim=(-1, -2)))
     assert rel(weighted_rmse_torch_channels(pred, tar), want) < 1e-6
     assert rel(weighted_rmse_torch(pred, tar), want.mean(0)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patchify_cat_equals_patchify_of_concatenation(dtype):
+    mode = mode_for(dtype)
+    B, H, W = 3, 24, 40
+    parts = [gen(B, 5, H, W, seed=140), gen(B, 1, H, W, seed=141), gen(1, 3, H, W, seed=142)]
+    cat = torch.cat([p.expand(B, -1, -1, -1) for p in parts], dim=1).contiguous()
+    assert torch.equal(ops.patchify_cat(parts, 4, mode), ops.patchify(cat, 4, 0, mode))
+    assert torch.equal(ops.patchify_cat([cat], 4, mode), ops.patchify(cat, 4, 0, mode))

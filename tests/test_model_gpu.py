@@ -226,3 +226,55 @@ def test_full_resolution_batch_independence():
     assert abs(l2 - (l0 + l1)) / abs(l2) < 1e-6
     for k in g2:
         assert O.rel_l2(g2[k].cpu(), (g0[k] + g1[k]).cpu()) < 2e-3, k
+
+
+def test_channel_groups_equal_concatenation():
+    """Conditioning inputs: feeding [field | zenith | static features] as channel groups must give
+    bit-identical predictions and parameter gradients to the reference's torch.cat input -- same im2col values, no copy --
+    including the batch-shared static group, the residual skip, and the MultiStepWrapper rollout."""
+    from types import SimpleNamespace
+    from swin_v2_weather_b200.networks.helpers import MultiStepWrapper
+    from swin_v2_weather_b200.utils.preprocess_utils import PreProcessor
+    torch.manual_seed(1)
+    B, H, W = 2, 72, 144
+    kw = dict(img_size=(H, W), patch_size=4, depths=(2,), num_heads=(2,), in_chans=9, out_chans=5, embed_dim=192,
+              img_window_ratio=8, drop_path_rate=0.0, full_pos_embed=True, rel_pos=False, residual=True)
+    model = SwinTransformerV2Cr(compute_mode="bf16", **kw).cuda().eval()
+    g = torch.Generator().manual_seed(7)
+    field, zen = torch.randn(B, 5, H, W, generator=g).cuda(), torch.rand(B, 1, H, W, generator=g).cuda()
+    lsm = (torch.rand(H, W, generator=g) > 0.7).long()
+    oro = torch.randn(H, W, generator=g)
+    params = SimpleNamespace(img_size=(H, W), add_landmask=True, add_orography=True, add_zenith=True, landmask=lsm, orography=oro)
+    pre = PreProcessor(params, "cuda").cuda()
+    tar = torch.randn(B, 5, H, W, generator=g).cuda()
+    groups, tar2, tzen = pre((field, tar, zen, zen))
+    assert isinstance(groups, tuple) and [t.shape[1] for t in groups] == [5, 1, 3] and groups[2].shape[0] == 1
+    params_cat = SimpleNamespace(**{**vars(params), "fuse_conditioning": False})
+    cat, _, _ = PreProcessor(params_cat, "cuda").cuda()((field, tar, zen, zen))
+    assert cat.shape == (B, 9, H, W)
+
+    def run(inp):
+        model.zero_grad(set_to_none=True)
+        out = model(inp)
+        out.square().mean().backward()
+        return out.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    o1, g1 = run(groups)
+    o2, g2 = run(cat)
+    assert torch.equal(o1, o2)
+    for k in g1:
+        assert O.rel_l2(g1[k].cpu(), g2[k].cpu()) < 1e-5, k      # fp32 atomics reorder; the inputs to every kernel are identical
+
+    # rollout: groups re-appended per step instead of two torch.cat per step
+    wrap = MultiStepWrapper(SimpleNamespace(n_future=1, add_orography=True, add_landmask=True), lambda p: model)
+    coszen = torch.rand(B, 1, H, W, generator=g).cuda()
+    model.zero_grad(set_to_none=True)
+    r1 = wrap(groups, coszen)
+    r1.square().mean().backward()
+    gr1 = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    r2 = wrap(cat, coszen)
+    r2.square().mean().backward()
+    assert torch.equal(r1, r2)
+    for k in gr1:
+        assert O.rel_l2(gr1[k].cpu(), model.get_parameter(k).grad.cpu()) < 2e-3, k
