@@ -74,7 +74,8 @@ def load() -> ctypes.CDLL:
 
 
 # kernels launched per C-ABI call (everything else launches exactly one); used for the launch counter
-_KERNELS_PER_CALL = {"swinb200_latw_l2_fwd": 2}
+# kernels launched per C-ABI call where it is not one (loss: reduce + finish; attention backward: <dO,O> pre-pass + main kernel)
+_KERNELS_PER_CALL = {"swinb200_latw_l2_fwd": 2, "swinb200_window_attn_bwd": 2}
 LAUNCH_COUNT = 0          # our kernels launched so far in this process
 PROFILE_HOOK = None       # optional callable(name, args) -> context manager; set by bench.py to time kernels
 
