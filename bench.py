@@ -114,6 +114,11 @@ class KernelTimer:
             backend, M, N, K = args[0], args[1], args[2], args[3]
             fam = "gemm_tcgen05" if backend == 1 else "gemm_simt"
             flops = 2.0 * M * N * K
+            # algorithmic bytes: both operands once + every output / epilogue operand once (swinb200_gemm argument order)
+            esz = 2 if args[10] == 1 else 4
+            epi = args[11]
+            out_b = {0: esz, 1: 2 * esz, 2: 2 * esz, 3: 8, 4: 4, 5: esz}.get(epi, esz)    # per output element
+            bytes_ = float(esz) * (M * K + N * K) + float(out_b) * M * N
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         yield
@@ -123,9 +128,10 @@ class KernelTimer:
     def summary(self):
         fam = {}
         for f, fl, by, s, e in self.records:
-            d = fam.setdefault(f, dict(ms=0.0, flops=0.0, launches=0))
+            d = fam.setdefault(f, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
+            d["bytes"] += by
             d["launches"] += 1
         return fam
 
@@ -301,7 +307,12 @@ def run_ours(args):
         roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM family: qkv/proj/fc1/fc2/patch-embed/head fwd, dgrad, wgrad)",
                 "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tf_sust"], 4), "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": gemm["launches"] / args.steps / 1.0,
+                # DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the 149 GEMM launches of
+                # one step (profiles/r1_b_gemm_traffic.csv, tools/ncu_gemm_traffic.sh), next to the algorithmic bytes per launch
+                "traffic": 567.0e6 if (B == 1 and args.mode == "bf16") else None,
+                "traffic_source": "profiles/r1_b_gemm_traffic.csv (ncu, batch 1: 410.7 MB read + 156.3 MB written per launch)",
+                "algorithmic_bytes_per_launch": round(gemm["bytes"] / gemm["launches"], 1),
+                "launches_per_step": gemm["launches"] / args.steps / 1.0,
                 "avg_launch_ms": round(gemm["ms"] / gemm["launches"], 4), "flops_per_launch": gemm["flops"] / gemm["launches"],
                 "share_of_step": round(gemm["ms"] / ms_total, 4)}
     families = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps}
