@@ -1202,21 +1202,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
     }
   };
-  // one operand gathered by four warps (w4 = 0..3) with a lane map that suits the 128-byte-aligned chunk stride: a warp
-  // instruction covers 8 rows x 4 consecutive chunks -- 64 contiguous bytes per token row from global, eight distinct
-  // 16-byte bank groups in shared memory
-  auto gather_w4 = [&](int op, const int* tk, int hd, int w4) {
-    const int nrb = (L + 7) / 8;
-    for (int it = w4; it < nrb * 3; it += 4) {
-      const int rb = it / 3, cg = it - rb * 3;
-      const int n = rb * 8 + (lane & 7), c = cg * 4 + (lane >> 3);
-      if (n < L) {
-        const __nv_bfloat16* src = (op < 3) ? qkv + (size_t)tk[n] * C3 + op * C + hd * D + c * 8
-                                            : d_o + (size_t)tk[n] * C + hd * D + c * 8;
-        cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
-      }
-    }
-  };
   auto fill_tok = [&](int item, int* tk) {
     const int hd = item % g.heads;
     const int ww = (item / g.heads) % g.nW;
@@ -1242,7 +1227,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int bb = item / (g.heads * g.nW);
     const int wh = ww_all / g.nWw, ww = ww_all - wh * g.nWw;
     fence_proxy_async_smem();    // earlier generic-proxy reads of these tiles are ordered before the async-proxy writes
-    if (first) mbar_arrive_expect_tx(ld_bar, (uint32_t)(op_hi - op_lo) * SM::kChunks * kBoxBytes * (uint32_t)L);
+    if (first) mbar_arrive_expect_tx(ld_bar, 4u * SM::kChunks * kBoxBytes * (uint32_t)L);
     for (int op = op_lo; op < op_hi; ++op) {
       const CUtensorMap* tm = (op < 3) ? &tm_qkv : &tm_do;
       const int chunk0 = ((op < 3) ? op * C + hd * D : hd * D) / 8;
@@ -1303,9 +1288,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   if (cur_box) {
     mbar_wait(ld_bar, ld_parity, 640);
     ld_parity ^= 1;
+  } else {
+    cp_async_wait_all();
+    fence_proxy_async_smem();
   }
-  cp_async_wait_all();          // Q^ / dO of a box item (gathered by the dv warpgroup under the previous dk epilogue), or everything
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   SWB_ACC(2);
@@ -1562,8 +1548,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // ... and Q^ / dO after the last dV / dK^ MMAs
     if (u == ntiles - 1 && has_next) {
       if (next_box) {
-        // Q^ / dO: TMA boxes with a 16-byte inner extent sustain only ~4.4 B/cycle, which would leave ~4 K cycles exposed at
-        // the top of the next item; the dv warpgroup gathers them with cp.async below, while the dk warpgroup is busy
+        if (tid == 0) { issue_boxes(0, 1, item_next, false); issue_boxes(3, 4, item_next, false); }
       } else {
         gather(0, 1, tok_next, head_next);
         gather(3, 4, tok_next, head_next);
@@ -1606,10 +1591,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           park_row<D>(sDS, r, acc);
         }
       }
-    }
-    if (half == 0 && u == ntiles - 1 && has_next && next_box) {
-      gather_w4(0, tok_next, head_next, warp);
-      gather_w4(3, tok_next, head_next, warp);
     }
     tc_fence_before();
     __syncthreads();
