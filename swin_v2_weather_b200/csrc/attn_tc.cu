@@ -1108,8 +1108,27 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
   }
 }
 
-// Persistent variant: shared-memory layout with a 128-byte-aligned chunk stride so every (operand, 16-byte chunk) column
-// of a window is one TMA box [8 elements x Ww x Wh] of the (B, H, W, channels) activation tensor.
+// Persistent variant.  Operand tiles (Q^, K^, V, dO) use 64-byte rows with the 64B swizzle: a [rows x 96] bf16 tile is
+// three 32-column chunks of [176 rows x 64 B], and one chunk of a window is ONE TMA box [32 elements x Ww x Wh] of the
+// (B, H, W, channels) activation tensor (64-byte rows move four times faster through the copy engine than the 16-byte
+// rows of the un-swizzled layout).  The same bytes serve as K-major operands (rows = m/n, k along the row: 8-row groups
+// 512 B apart, k advances 32 B inside the row, 32-k chunks a chunk stride apart) and as MN-major operands (rows = k:
+// 8-k groups 512 B apart, 32-wide n chunks a chunk stride apart, k advances 16 rows = 1024 B).
+constexpr int kCS64 = kMaxLP * 64;          // chunk stride: 11,264 B = 22 x 512
+__host__ __device__ constexpr uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61) /* SWIZZLE_64B */;
+}
+__device__ __forceinline__ uint64_t opnd_kmajor(uint32_t base, int k, int row0) {   // k-th 16-wide k step, rows from row0
+  return umma_desc_sw64(base + (uint32_t)((k >> 1) * kCS64 + (k & 1) * 32 + row0 * 64), 16, 512);
+}
+__device__ __forceinline__ uint64_t opnd_mnmajor(uint32_t base, int k) {             // k-th group of 16 rows (= k dimension)
+  return umma_desc_sw64(base + (uint32_t)(k * 1024), kCS64, 512);
+}
+// byte offset of the 16-byte piece `piece` (0..11) of row `row` inside an operand tile
+__device__ __forceinline__ uint32_t opnd_off(int row, int piece) {
+  return (uint32_t)((piece >> 2) * kCS64 + row * 64 + (((piece & 3) ^ ((row >> 1) & 3)) << 4));
+}
 template <int D>
 struct Bwd2Smem {
   static constexpr int kChunks = D / 8;
@@ -1187,7 +1206,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int op = i / ((LP - L) * SM::kChunks);
     const int rem = i - op * (LP - L) * SM::kChunks;
     const int c = rem / (LP - L), r = L + rem % (LP - L);
-    *reinterpret_cast<uint4*>(smem + op * SM::kTile + c * SM::kCS + r * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + op * SM::kTile + opnd_off(r, c)) = make_uint4(0, 0, 0, 0);
   }
   if (tid < 32) dsc_heads[tid] = 0.f;
   // operands op_lo..op_hi-1 (0 Q^, 1 K^, 2 V, 3 dO) of the (window, head) whose token table is `tk`
@@ -1199,7 +1218,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const int n = rem / SM::kChunks, c = rem - n * SM::kChunks;
       const __nv_bfloat16* src = (op < 3) ? qkv + (size_t)tk[n] * C3 + op * C + hd * D + c * 8
                                           : d_o + (size_t)tk[n] * C + hd * D + c * 8;
-      cp_async16(smem + op * SM::kTile + c * SM::kCS + n * 16, src);
+      cp_async16(smem + op * SM::kTile + opnd_off(n, c), src);
     }
   };
   auto fill_tok = [&](int item, int* tk) {
@@ -1219,7 +1238,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int wh = ww_all / g.nWw, ww = ww_all - wh * g.nWw;
     return !((g.s0 > 0 && (wh + 1) * g.Wh + g.s0 > g.H) || (g.s1 > 0 && (ww + 1) * g.Ww + g.s1 > g.W));
   };
-  constexpr uint32_t kBoxBytes = 16;   // x L rows, per (operand, chunk)
+  constexpr uint32_t kBoxBytes = 64;   // x L rows, per (operand, 32-column chunk)
+  constexpr int kBoxes = D / 32;
   // one thread: boxes of operands [op_lo, op_hi) of `item`; `first` registers the item's total byte count
   auto issue_boxes = [&](int op_lo, int op_hi, int item, bool first) {
     const int hd = item % g.heads;
@@ -1227,13 +1247,13 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int bb = item / (g.heads * g.nW);
     const int wh = ww_all / g.nWw, ww = ww_all - wh * g.nWw;
     fence_proxy_async_smem();    // earlier generic-proxy reads of these tiles are ordered before the async-proxy writes
-    if (first) mbar_arrive_expect_tx(ld_bar, 4u * SM::kChunks * kBoxBytes * (uint32_t)L);
+    if (first) mbar_arrive_expect_tx(ld_bar, 4u * kBoxes * kBoxBytes * (uint32_t)L);
     for (int op = op_lo; op < op_hi; ++op) {
       const CUtensorMap* tm = (op < 3) ? &tm_qkv : &tm_do;
-      const int chunk0 = ((op < 3) ? op * C + hd * D : hd * D) / 8;
-#pragma unroll 4
-      for (int c = 0; c < SM::kChunks; ++c)
-        tma_load_5d(smem + op * SM::kTile + c * SM::kCS, tm, ld_bar, 0, chunk0 + c, ww * g.Ww + g.s1, wh * g.Wh + g.s0, bb);
+      const int chunk0 = ((op < 3) ? op * C + hd * D : hd * D) / 32;
+#pragma unroll
+      for (int c = 0; c < kBoxes; ++c)
+        tma_load_5d(smem + op * SM::kTile + c * kCS64, tm, ld_bar, 0, chunk0 + c, ww * g.Ww + g.s1, wh * g.Wh + g.s0, bb);
     }
   };
   bool cur_box = false;
@@ -1311,12 +1331,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)      // S = Q^_t K^T
-        umma_bf16_ss(tmem_base, umma_desc_nosw(q0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
-                     umma_desc_nosw(k0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+        umma_bf16_ss(tmem_base, opnd_kmajor(q0, k, t * 128), opnd_kmajor(k0, k, 0), idesc_s, k > 0);
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)      // dP = dO_t V^T
-        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(g0 + 2 * k * SM::kCS + t * 2048, SM::kCS, 128),
-                     umma_desc_nosw(v0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+        umma_bf16_ss(tmem_base + kMaxLP, opnd_kmajor(g0, k, t * 128), opnd_kmajor(v0, k, 0), idesc_s, k > 0);
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 600 + t);
@@ -1412,7 +1430,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
       for (int k = 0; k < LP / 16; ++k)     // dQ^_t = dS K^   (K^ read n-major: rows = keys = k-dimension)
         umma_bf16_ss(tmem_base, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
-                     umma_desc_nosw(k0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+                     opnd_mnmajor(k0, k), idesc_o, k > 0);
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 610 + t);
@@ -1439,7 +1457,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
           float t8[8];
-          ld8(reinterpret_cast<const __nv_bfloat16*>(sQ + c * SM::kCS + n * 16), t8);
+          ld8(reinterpret_cast<const __nv_bfloat16*>(sQ + opnd_off(n, c)), t8);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             qh[c * 8 + e] = t8[e];
@@ -1465,12 +1483,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)      // S^T = K^_u Q^T
-        umma_bf16_ss(tmem_base, umma_desc_nosw(k0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
-                     umma_desc_nosw(q0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+        umma_bf16_ss(tmem_base, opnd_kmajor(k0, k, u * 128), opnd_kmajor(q0, k, 0), idesc_s, k > 0);
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)      // dP^T = V_u dO^T
-        umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(v0 + 2 * k * SM::kCS + u * 2048, SM::kCS, 128),
-                     umma_desc_nosw(g0 + 2 * k * SM::kCS, SM::kCS, 128), idesc_s, k > 0);
+        umma_bf16_ss(tmem_base + kMaxLP, opnd_kmajor(v0, k, u * 128), opnd_kmajor(g0, k, 0), idesc_s, k > 0);
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 620 + u);
@@ -1535,10 +1551,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
       for (int k = 0; k < LP / 16; ++k)     // dV_u = P^T dO   (dO read n-major: rows = queries = k-dimension)
         umma_bf16_ss(tmem_base, umma_desc_nosw(p0 + 2 * k * SM::kPCS, SM::kPCS, 128),
-                     umma_desc_nosw(g0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+                     opnd_mnmajor(g0, k), idesc_o, k > 0);
       for (int k = 0; k < LP / 16; ++k)     // dK^_u = dS^T Q^
         umma_bf16_ss(tmem_base + kMaxLP, umma_desc_nosw(ds0 + 2 * k * SM::kPCS, SM::kPCS, 128),
-                     umma_desc_nosw(q0 + k * 256, 128, SM::kCS), idesc_o, k > 0);
+                     opnd_mnmajor(q0, k), idesc_o, k > 0);
       umma_commit(bar);
     }
     mbar_wait(bar, parity, 630 + u);
@@ -1648,7 +1664,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
-// (B, H, W, channels) bf16 activation seen as [8 | channels/8 | W | H | B]; one box = the 16-byte chunk column of a window
+// (B, H, W, channels) bf16 activation seen as [32 | channels/32 | W | H | B]; one box = a 32-channel (64-byte) column of a
+// window, written 64B-swizzled
 static int make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int channels, int Wh, int Ww) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
@@ -1656,12 +1673,12 @@ static int make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int 
     return SWINB200_ERR_CUDA;
   }
   const cuuint64_t row = (cuuint64_t)channels * 2;
-  cuuint64_t dims[5] = {8, (cuuint64_t)channels / 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[4] = {16, row, row * W, row * W * H};
-  cuuint32_t box[5] = {8, 1, (cuuint32_t)Ww, (cuuint32_t)Wh, 1};
+  cuuint64_t dims[5] = {32, (cuuint64_t)channels / 32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[4] = {64, row, row * W, row * W * H};
+  cuuint32_t box[5] = {32, 1, (cuuint32_t)Ww, (cuuint32_t)Wh, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (window map) failed (%d)", (int)r);
