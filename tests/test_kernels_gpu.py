@@ -615,3 +615,16 @@ def test_patchify_cat_equals_patchify_of_concatenation(dtype):
     cat = torch.cat([p.expand(B, -1, -1, -1) for p in parts], dim=1).contiguous()
     assert torch.equal(ops.patchify_cat(parts, 4, mode), ops.patchify(cat, 4, 0, mode))
     assert torch.equal(ops.patchify_cat([cat], 4, mode), ops.patchify(cat, 4, 0, mode))
+
+
+def test_alternate_kernel_variants_in_a_fresh_process():
+    """The env-selected variants (first-generation attention kernels, single-CTA statically scheduled GEMM) are read once
+    per process, so they are exercised in a child process: same parity tests, different kernels."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SWINB200_ATTN_FWD="1", SWINB200_ATTN_BWD="1", SWINB200_GEMM_PAIR="0")
+    sel = "test_window_attention_tcgen05 or test_gemm_tcgen05 or test_gemm_tcgen05_split_k or persistent_many_tiles"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
