@@ -23,9 +23,33 @@ def test_library_loads_and_exports_header_symbols():
     assert len(syms) >= 17
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in swinb200.h but not exported"
+    assert "swinb200_adam_step" in syms and "swinb200_patchify_cat" in syms
     # every prototype bound by the Python side is declared in the header, and vice versa
     bound = set(_lib.PROTOTYPES) | {"swinb200_version", "swinb200_last_error"}
     assert bound == set(syms), bound ^ set(syms)
+
+
+def test_ctypes_prototypes_have_the_arity_of_the_header():
+    """A drifting argument list would shift every later pointer by one slot: count them."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "swinb200.h")).read(), flags=re.S)
+    decls = re.findall(r"\bint\s+(swinb200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) >= 17
+    for name, args in decls:
+        n = len([a for a in args.replace("\n", " ").split(",") if a.strip() and a.strip() != "void"])
+        if name in _lib.PROTOTYPES:
+            assert n == len(_lib.PROTOTYPES[name]), (name, n, len(_lib.PROTOTYPES[name]))
+
+
+def test_new_entry_points_reject_bad_arguments():
+    lib = _lib.load()
+    assert lib.swinb200_adam_step(1, None, None, None, None, None, None, 1e-3, 0.9, 0.95, 1e-8, 0.0, 1, None, None, None) == 1
+    assert b"null table" in lib.swinb200_last_error()
+    arr = (ctypes.c_void_p * 1)(16)
+    n = (ctypes.c_longlong * 1)(8)
+    assert lib.swinb200_adam_step(1, arr, arr, arr, arr, None, n, 1e-3, 0.9, 0.95, 1e-8, 0.0, 0, None, None, None) == 1
+    assert b"step counts from 1" in lib.swinb200_last_error()
+    assert lib.swinb200_patchify_cat(9, arr, None, None, None, 1, 1, 8, 8, 4, None) == 1
+    assert b"sources" in lib.swinb200_last_error()
 
 
 def test_argument_errors_come_back_as_codes_not_crashes():
