@@ -11,7 +11,9 @@ batch 1 per GPU, data-parallel over N B200s.
 `e2e`        : same metric through the public model API from pinned HOST buffers: per step the H2D copy of that
                step's input + target and the D2H read of the loss are inside the timed region.
 `roofline`   : the dominant kernel family, timed live with CUDA events inside the timed region.
-`cpu_baseline`: the CPU oracle (a port of the reference algorithm) on the host cores, bounded sample.
+`cpu_baseline`: the CPU oracle (a port of the reference algorithm) on the host cores, bounded sample (1/10 sample: all 12 blocks
+               on 40 of the 400 windows).  `gpu_eager_baseline`: the same oracle as eager PyTorch on the GPU under bf16 autocast.
+`gemm_variants` / `attn_pct_tc_peak`: per-shape GEMM table and the attention kernels against tensor and HBM peaks.
 """
 from __future__ import annotations
 
@@ -110,6 +112,15 @@ class KernelTimer:
             yield
             return
         flops = bytes_ = 0.0
+        variant = None
+        if fam in ("attn_fwd", "attn_bwd"):
+            # window attention FLOPs with the UNPADDED window length: fwd 4 nW h L^2 d, bwd 10 nW h L^2 d
+            if fam == "attn_fwd":
+                Bq, H, W, C, heads, Wh, Ww = args[7:14]
+            else:
+                Bq, H, W, C, heads, Wh, Ww = args[13:20]
+            L = Wh * Ww
+            flops = (4.0 if fam == "attn_fwd" else 10.0) * Bq * (H // Wh) * (W // Ww) * heads * L * L * (C // heads)
         if fam == "gemm":
             backend, M, N, K = args[0], args[1], args[2], args[3]
             fam = "gemm_tcgen05" if backend == 1 else "gemm_simt"
@@ -119,21 +130,39 @@ class KernelTimer:
             epi = args[11]
             out_b = {0: esz, 1: 2 * esz, 2: 2 * esz, 3: 8, 4: 4, 5: esz}.get(epi, esz)    # per output element
             bytes_ = float(esz) * (M * K + N * K) + float(out_b) * M * N
+            epi_name = {0: "bias", 1: "bias_gelu", 2: "dgelu", 3: "add_f32", 4: "f32", 5: "bias_qknorm"}.get(epi, str(epi))
+            variant = f"M{M}_N{N}_K{K}_a{args[5]}b{args[8]}_{epi_name}" + (f"_splitk{args[20]}" if args[20] > 1 else "")
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         yield
         e.record()
-        self.records.append((fam, flops, bytes_, s, e))
+        self.records.append((fam, flops, bytes_, s, e, variant))
 
     def summary(self):
-        fam = {}
-        for f, fl, by, s, e in self.records:
-            d = fam.setdefault(f, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            d["ms"] += s.elapsed_time(e)
-            d["flops"] += fl
-            d["bytes"] += by
-            d["launches"] += 1
+        fam, var = {}, {}
+        for f, fl, by, s, e, v in self.records:
+            ms = s.elapsed_time(e)
+            for key, table in ((f, fam), (v, var)):
+                if key is None:
+                    continue
+                d = table.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+                d["ms"] += ms
+                d["flops"] += fl
+                d["bytes"] += by
+                d["launches"] += 1
+        self.variants = var
         return fam
+
+
+def gemm_traffic(B, mode):
+    """DRAM bytes per GEMM launch from the committed ncu capture (never a literal): profiles/gemm_traffic.json is written
+    by tools/traffic_summary.py from the ncu CSV named inside it."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if not (B == 1 and mode == "bf16" and os.path.exists(p)):
+        return {"traffic": None, "traffic_source": None}
+    d = json.load(open(p))
+    return {"traffic": d["bytes_per_launch"], "traffic_source": f"{d['source']} ({d['when']}; {d['launches']} launches, "
+            f"{d['read_mb_per_launch']:.1f} MB read + {d['write_mb_per_launch']:.1f} MB written per launch)"}
 
 
 def make_model(device, compute_mode="bf16"):
@@ -307,16 +336,31 @@ def run_ours(args):
         roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM family: qkv/proj/fc1/fc2/patch-embed/head fwd, dgrad, wgrad)",
                 "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tf_sust"], 4), "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
-                # DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the 149 GEMM launches of
-                # one step (profiles/r1_b_gemm_traffic.csv, tools/ncu_gemm_traffic.sh), next to the algorithmic bytes per launch
-                "traffic": 567.0e6 if (B == 1 and args.mode == "bf16") else None,
-                "traffic_source": "profiles/r1_b_gemm_traffic.csv (ncu, batch 1: 410.7 MB read + 156.3 MB written per launch)",
+                # DRAM bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM launches of one
+                # step (tools/ncu_gemm_traffic.sh -> tools/traffic_summary.py -> profiles/gemm_traffic.json), next to the
+                # algorithmic bytes per launch
+                **gemm_traffic(B, args.mode),
                 "algorithmic_bytes_per_launch": round(gemm["bytes"] / gemm["launches"], 1),
                 "launches_per_step": gemm["launches"] / args.steps / 1.0,
                 "avg_launch_ms": round(gemm["ms"] / gemm["launches"], 4), "flops_per_launch": gemm["flops"] / gemm["launches"],
                 "share_of_step": round(gemm["ms"] / ms_total, 4)}
     families = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["launches"] / args.steps}
                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    # every GEMM template variant / shape on its own line, so a slow epilogue cannot hide inside the family average
+    gemm_variants = {k: {"launches_per_step": v["launches"] / args.steps, "gflop": round(v["flops"] / v["launches"] / 1e9, 1),
+                         "us": round(v["ms"] / v["launches"] * 1e3, 1), "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1),
+                         "frac_of_sustained": round(v["flops"] / (v["ms"] / 1e3) / 1e12 / peaks["tf_sust"], 3)}
+                     for k, v in sorted(timer.variants.items(), key=lambda kv: -kv[1]["ms"]) if v["ms"] > 0}
+    # BASELINE metric, second half: attention as % of the tensor-core peak (and of its HBM roofline, which bounds it)
+    attn = {}
+    for key, nbytes in (("attn_fwd", 4 * T * 768 * 2), ("attn_bwd", 8 * T * 768 * 2)):
+        a = fam.get(key)
+        if a and a["ms"] > 0:
+            tf = a["flops"] / (a["ms"] / 1e3) / 1e12
+            gbs = nbytes * B * a["launches"] / (a["ms"] / 1e3) / 1e9
+            attn[key] = {"us_per_launch": round(a["ms"] / a["launches"] * 1e3, 1), "tflops": round(tf, 1),
+                         "pct_tc_peak_sustained": round(100 * tf / peaks["tf_sust"], 2), "pct_tc_peak_burst": round(100 * tf / peaks["tf_burst"], 2),
+                         "hbm_gbs": round(gbs, 0), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
 
     # ---- optimizer step, reported separately ("optimizer step reported separately"; 8(f) rank 1) ----------
     optimizer = None
@@ -371,7 +415,15 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_samples_per_s(budget_s=60.0)
+        cpu = cpu_reference_samples_per_s(steps=2, warmup=1)
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        del model, ddp, lossf, x_res, t_res, bufs
+        torch.cuda.empty_cache()
+        try:
+            eager = gpu_eager_samples_per_s(dev, steps=3, warmup=1)
+        except Exception as exc:   # the baseline must never take the main line down
+            eager = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     out = {
         "metric": "samples/s (fwd+bwd) 73ch 721x1440 SwinV2-d12", "value": round(value, 4), "unit": "samples/s",
@@ -389,6 +441,9 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roof,
         "kernel_families": families,
+        "gemm_variants": gemm_variants,
+        "attn_pct_tc_peak": attn,
+        "gpu_eager_baseline": eager,
         "optimizer_step": optimizer,
         "model_tflops": round(value * FLOPS_FWD_BWD / 1e12 / world, 1),
         "model_frac_of_sustained_peak": round(value * FLOPS_FWD_BWD / 1e12 / world / peaks["tf_sust"], 4),
@@ -409,72 +464,101 @@ def ops_attn_is_tc(mode_name):
 # ==============================================================================================================
 # reference arm / cpu baseline: the reference algorithm (oracle port) on the host CPU cores
 # ==============================================================================================================
-def _oracle_pass(depth, threads):
-    """One fwd + loss + bwd of the oracle at full resolution with `depth` blocks; returns seconds."""
+# The CPU sample: the FULL 12-block model on ten 72 x 144-pixel tiles of a 73-channel field (a batch of 10) = 10 x 4 = 40 of the
+# 400 windows (6,480 of the 64,800 tokens) of a sample, same 9 x 18 windows and shift pattern.  Every operator of the path is
+# per token or per window (PatchEmbed, LayerNorm, the MLP, window attention, head, loss rows), so one pass is exactly 1/10 of
+# the work of one sample -- no intercept, no depth extrapolation -- and every timed step is the same real fwd + loss + bwd.
+TILE = (72, 144)
+TILES_PER_STEP = 10
+BAND_FRACTION = TILES_PER_STEP * TILE[0] * TILE[1] / (720.0 * 1440.0)
+
+
+def _band_problem(device="cpu"):
     from oracle import swinv2_oracle as O
-    cfg = O.SwinConfig(**{**CFG, "depth": depth, "drop_path_rate": 0.0})
-    sd = O.init_state_dict(cfg, seed=0)
+    cfg = O.SwinConfig(**{**CFG, "img_size": TILE, "window_ratio": 8, "drop_path_rate": 0.0})
+    assert cfg.window == (9, 18) and cfg.grid == (18, 36) and abs(BAND_FRACTION - 0.1) < 1e-12
+    sd = {k: v.to(device) for k, v in O.init_state_dict(cfg, seed=0).items()}
     g = torch.Generator().manual_seed(1234)
-    x = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous()
-    t = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous()
-    chw = torch.ones(73) / 73
-    t0 = time.perf_counter()
-    O.loss_and_grads(x, t, sd, cfg, chw, relative=True)
-    return time.perf_counter() - t0
+    x = torch.randn(TILES_PER_STEP, 73, *TILE, generator=g).to(device)
+    t = torch.randn(TILES_PER_STEP, 73, *TILE, generator=g).to(device)
+    return O, cfg, sd, x, t, (torch.ones(73) / 73).to(device)
 
 
-def cpu_reference_samples_per_s(budget_s=60.0):
+def _time_cpu_band(steps, warmup):
+    """`steps` timed passes (after `warmup`) of the oracle on the band; returns (seconds per pass list, threads)."""
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    t1 = _oracle_pass(1, threads)
-    t2 = _oracle_pass(2, threads) if t1 < budget_s else None
-    if t2 is not None:
-        per_block = max(t2 - t1, 1e-3)
-        t12 = t1 + 11 * per_block
-        sample = (f"oracle fp32 fwd+loss+bwd at full 73x720x1440 resolution with depth 1 ({t1:.1f} s) and depth 2 ({t2:.1f} s), "
-                  f"extrapolated linearly to depth 12 ({t12:.1f} s)")
-    else:
-        t12 = t1 * 12
-        sample = f"oracle fp32 fwd+loss+bwd at depth 1 ({t1:.1f} s) scaled x12"
-    return {"value": round(1.0 / t12, 5), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+    O, cfg, sd, x, t, chw = _band_problem()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(x, t, sd, cfg, chw, relative=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, threads
+
+
+CPU_SAMPLE = ("oracle (port of the reference algorithm, torch fp32 on the host cores): full 12-block model, fwd + 'squared geometric "
+              "l2' loss + bwd, on ten 72x144-pixel tiles of a 73-channel field = 40 of the 400 windows of one sample; all "
+              "operators are per token / per window, so one pass = 1/10 sample")
+
+
+def cpu_reference_samples_per_s(steps=2, warmup=1):
+    times, threads = _time_cpu_band(steps, warmup)
+    sec = sum(times) / len(times)
+    return {"value": round(BAND_FRACTION / sec, 5), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": CPU_SAMPLE + f"; {len(times)} timed passes of {sec:.2f} s after {warmup} warm-up"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    # calibration (untimed): per-block cost = t(depth 2) - t(depth 1)
-    t1c = _oracle_pass(1, threads)
-    t2c = _oracle_pass(2, threads)
-    per_block = max(t2c - t1c, 1e-3)
-    budget = 240.0
-    done_w = 0
-    t_start = time.perf_counter()
-    for _ in range(args.warmup):
-        if time.perf_counter() - t_start > budget / 4:
-            break
-        _oracle_pass(1, threads)
-        done_w += 1
-    times = []
-    for _ in range(args.steps):
-        if times and time.perf_counter() - t_start > budget:
-            break
-        times.append(_oracle_pass(1, threads))
-    t1 = sum(times) / len(times)
-    t12 = t1 + 11 * per_block
-    value = 1.0 / t12
-    sample = (f"each step = oracle (port of the reference algorithm, torch fp32 CPU) fwd+loss+bwd at full 73x720x1440 resolution, "
-              f"depth 1 ({t1:.1f} s avg over {len(times)} steps); per-block cost {per_block:.1f} s calibrated once from a depth-2 "
-              f"pass; value = 1 / (t_depth1 + 11 * t_block) = depth-12 extrapolation ({t12:.1f} s/sample)")
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    times, threads = _time_cpu_band(steps, warmup)
+    total = sum(times)
+    value = steps * BAND_FRACTION / total
     out = {"impl": "reference", "metric": "samples/s (fwd+bwd) 73ch 721x1440 SwinV2-d12", "value": round(value, 5),
-           "unit": "samples/s", "n_gpus": args.gpus, "steps": len(times), "warmup": done_w, "ms_per_step": round(t12 * 1e3, 1),
+           "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(total / steps * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "swin_73var_geo_depth12 fwd+loss+bwd, batch 1, host CPU", "global_batch": 1, "parallelism": "cpu"},
-           "cpu_baseline": {"value": round(value, 5), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+           "config": {"workload": "swin_73var_geo_depth12 fwd+loss+bwd on the host CPU; each step = 1/10 of a sample (ten 72x144 tiles = 40 "
+                                  "windows, all 12 blocks)", "samples_per_step": BAND_FRACTION, "global_batch": 1, "parallelism": "cpu"},
+           "step_seconds": [round(v, 3) for v in times],
+           "cpu_baseline": {"value": round(value, 5), "unit": "samples/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE},
            "e2e": {"value": round(value, 5), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
+
+
+def gpu_eager_samples_per_s(dev, steps=3, warmup=1):
+    """The bar the reference itself would set on this GPU: the same algorithm as plain
+    eager PyTorch on the B200 under bf16 autocast -- the oracle port moved to the device (the reference tree does not exist
+    on the GPU box), full 73x720x1440 sample, all 12 blocks, fwd + loss + bwd, CUDA-event timed."""
+    from oracle import swinv2_oracle as O
+    cfg = O.SwinConfig(**{**CFG, "drop_path_rate": 0.0})
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous().to(dev)
+    t = torch.randn(1, 73, FIELD_ROWS, 1440, generator=g)[:, :, :720].contiguous().to(dev)
+    chw = (torch.ones(73) / 73).to(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+
+    def one():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            O.loss_and_grads(x, t, sd, cfg, chw, relative=True)
+
+    for _ in range(warmup):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(1e3 / ms, 3), "unit": "samples/s", "ms_per_step": round(ms, 2), "steps": steps, "warmup": warmup,
+            "kind": "oracle port, eager PyTorch on cuda under bf16 autocast (cuBLAS / cuDNN / ATen kernels, no kernels of this repo)",
+            "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
 
 
 def main():
@@ -482,14 +566,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--mode", default="bf16", help="compute mode: bf16 | bf16_simt | fp32")
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager":
+        print(json.dumps({"impl": "eager", **gpu_eager_samples_per_s(torch.device("cuda", 0), args.steps, args.warmup)}), flush=True)
     else:
         run_ours(args)
 

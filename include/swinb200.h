@@ -70,6 +70,18 @@ int swinb200_patchify_cat(int n_src, const float* const* srcs, const int* chans,
                           void* out, int act_dtype, int B, int Hi, int Wi, int P, void* stream);
 int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out,
                         int B, int Co, int Hi, int Wi, int P, int order, void* stream);
+/* Input z-score folded into the same passes: `mean` / `std` are (C,) fp32 device arrays over the
+ *   concatenated channels; every image value becomes (x - mean[c]) / std[c] on its way into the im2col -- the per-channel
+ *   normalisation the loaders apply on the GPU before the model sees a field (utils/data_loader_era5_dali.py:77-90,
+ *   utils/data_loader_era5.py:98-107).  Channels that must pass through unchanged carry mean 0 / std 1 ((x-0)/1 == x).
+ *   swinb200_unpatchify_norm applies the same to the residual skip (swinv2_global.py:795-802) when it is the raw field.
+ *   NULL statistics = the plain entry points above. */
+int swinb200_patchify_cat_norm(int n_src, const float* const* srcs, const int* chans, const long long* batch_strides,
+                               const float* mean, const float* std, void* out, int act_dtype, int B, int Hi, int Wi,
+                               int P, void* stream);
+int swinb200_unpatchify_norm(const void* y, int act_dtype, const float* skip, int skip_chans, const float* skip_mean,
+                             const float* skip_std, float* out, int B, int Co, int Hi, int Wi, int P, int order,
+                             void* stream);
 
 /* ---- GEMM ---------------------------------------------------------------------------------------
  * D[M,N] = epilogue( sum_k A(m,k) * B(n,k) ).
@@ -149,6 +161,21 @@ int swinb200_latw_l2_fwd(const float* prd, const float* tar, const float* qw, co
 int swinb200_latw_l2_bwd(const float* prd, const float* tar, const float* qw, const float* chw,
                          const float* num, const float* den, const float* gloss, int relative, int squared,
                          float* dprd, int B, int C, int H, int W, void* stream);
+
+/* ---- L1 loss family and validation anomaly correlation ---------------------------
+ * latw_l1_fwd: sums[b,c] = {sum_hw qw[h] |p-t|, sum_hw qw[h] |t|};  loss = sum_bc chw[c] * (relative ? s0/s1 : s0)
+ *   == LossHandler 'l1' / 'geometric l1' -> GeometricLpLoss(p=1).abs/.rel (utils/losses.py:116-124, 188-232).
+ * latw_l1_bwd: dprd = gloss * chw[c] * qw[h] * sign(p-t) / (relative ? s1 : 1).
+ * Pole-masked variants of every loss ('pole-masked', utils/losses.py:49-52, utils/grids.py:96-99) are the same kernels
+ *   with the first / last rows of qw set to zero by the caller.
+ * latw_acc: sums[b,c] = {sum qw p t, sum qw p p, sum qw t t};  acc[b,c] = s0 / sqrt(s1 * s2)
+ *   == weighted_acc_torch_channels (utils/weighted_acc_rmse.py:89-99).  sums (B*C*3) and acc (B*C) are fp32 outputs. */
+int swinb200_latw_l1_fwd(const float* prd, const float* tar, const float* qw, const float* chw, int relative,
+                         float* sums, float* loss, int B, int C, int H, int W, void* stream);
+int swinb200_latw_l1_bwd(const float* prd, const float* tar, const float* qw, const float* chw, const float* sums,
+                         const float* gloss, int relative, float* dprd, int B, int C, int H, int W, void* stream);
+int swinb200_latw_acc(const float* prd, const float* tar, const float* qw, float* sums, float* acc, int B, int C,
+                      int H, int W, void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------
  * One fused multi-tensor pass of torch.optim.Adam(lr, betas, eps, weight_decay, amsgrad=False) as the reference

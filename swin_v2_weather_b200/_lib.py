@@ -25,6 +25,11 @@ PROTOTYPES = {
     "swinb200_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "swinb200_patchify_cat": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "swinb200_unpatchify": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "swinb200_patchify_cat_norm": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "swinb200_unpatchify_norm": [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "swinb200_latw_l1_fwd": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "swinb200_latw_l1_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
+    "swinb200_latw_acc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "swinb200_gemm": [_I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "swinb200_ln_residual_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, c_float, _P],
     "swinb200_ln_residual_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -75,7 +80,7 @@ def load() -> ctypes.CDLL:
 
 # kernels launched per C-ABI call (everything else launches exactly one); used for the launch counter
 # kernels launched per C-ABI call where it is not one (loss: reduce + finish; attention backward: <dO,O> pre-pass + main kernel)
-_KERNELS_PER_CALL = {"swinb200_latw_l2_fwd": 2, "swinb200_window_attn_bwd": 2}
+_KERNELS_PER_CALL = {"swinb200_latw_l2_fwd": 2, "swinb200_window_attn_bwd": 2, "swinb200_latw_l1_fwd": 2, "swinb200_latw_acc": 2}
 LAUNCH_COUNT = 0          # our kernels launched so far in this process
 PROFILE_HOOK = None       # optional callable(name, args) -> context manager; set by bench.py to time kernels
 

@@ -145,7 +145,8 @@ struct PatchSrcs {
   int n;
 };
 template <typename T>
-__global__ void __launch_bounds__(256) patchify_cat_kernel(const __grid_constant__ PatchSrcs src, T* __restrict__ out, int B, int C,
+__global__ void __launch_bounds__(256) patchify_cat_kernel(const __grid_constant__ PatchSrcs src, const float* __restrict__ mean,
+                                                           const float* __restrict__ stdv, T* __restrict__ out, int B, int C,
                                                            int Hi, int Wi, int ntok) {
   constexpr int P = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,7 +167,11 @@ __global__ void __launch_bounds__(256) patchify_cat_kernel(const __grid_constant
     const int t = t0 + tok;
     const int j = t % W, i = (t / W) % H, b = t / (W * H);
     const float* base = src.ptr[s] + (size_t)b * src.bstride[s] + ((size_t)(c - src.c0[s]) * Hi + (i * P + p)) * Wi + j * P;
-    const float4 v = *reinterpret_cast<const float4*>(base);
+    float4 v = *reinterpret_cast<const float4*>(base);
+    if (mean != nullptr) {   // z-score of the loaders (data_loader_era5_dali.py:77-90): (x - mean_c) / std_c, true division
+      const float m = __ldg(mean + c), sd = __ldg(stdv + c);
+      v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
+    }
     T* d = tile + (size_t)tok * pitch + (c * P + p) * P;
     Act<T>::st(d + 0, v.x); Act<T>::st(d + 1, v.y); Act<T>::st(d + 2, v.z); Act<T>::st(d + 3, v.w);
   }
@@ -182,8 +187,9 @@ __global__ void __launch_bounds__(256) patchify_cat_kernel(const __grid_constant
 
 template <typename T, int ORDER>
 __global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y, const float* __restrict__ skip,
-                                                         int skip_chans, float* __restrict__ out, int B, int Co, int Hi,
-                                                         int Wi, int ntok) {
+                                                         int skip_chans, const float* __restrict__ smean,
+                                                         const float* __restrict__ sstd, float* __restrict__ out, int B, int Co,
+                                                         int Hi, int Wi, int ntok) {
   constexpr int P = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
@@ -221,7 +227,11 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const T* __restrict__ y
     }
     const size_t pix = (size_t)(i * P + p) * Wi + j * P;
     if (skip != nullptr) {
-      const float4 s = *reinterpret_cast<const float4*>(skip + ((size_t)b * skip_chans + c) * Hi * Wi + pix);
+      float4 s = *reinterpret_cast<const float4*>(skip + ((size_t)b * skip_chans + c) * Hi * Wi + pix);
+      if (smean != nullptr) {   // the skip is the raw field: z-score it exactly as the im2col does
+        const float m = __ldg(smean + c), sd = __ldg(sstd + c);
+        s.x = (s.x - m) / sd; s.y = (s.y - m) / sd; s.z = (s.z - m) / sd; s.w = (s.w - m) / sd;
+      }
       v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
     }
     *reinterpret_cast<float4*>(out + ((size_t)b * Co + c) * Hi * Wi + pix) = v;
@@ -765,6 +775,13 @@ extern "C" int swinb200_patchify(const float* img, void* out, int act_dtype, int
 
 extern "C" int swinb200_patchify_cat(int n_src, const float* const* srcs, const int* chans, const long long* batch_strides, void* out,
                                      int act_dtype, int B, int Hi, int Wi, int P, void* stream) {
+  return swinb200_patchify_cat_norm(n_src, srcs, chans, batch_strides, nullptr, nullptr, out, act_dtype, B, Hi, Wi, P, stream);
+}
+
+extern "C" int swinb200_patchify_cat_norm(int n_src, const float* const* srcs, const int* chans, const long long* batch_strides,
+                                          const float* mean, const float* stdv, void* out, int act_dtype, int B, int Hi, int Wi, int P,
+                                          void* stream) {
+  SWB_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "patchify_cat: mean and std must be given together");
   SWB_CHECK_ARG(n_src >= 1 && n_src <= kPatchMaxSrc && srcs && chans && batch_strides && out, "patchify_cat: 1..%d sources", kPatchMaxSrc);
   SWB_CHECK_ARG(P == 4, "patchify_cat: only patch_size 4 is supported (got %d)", P);
   SWB_CHECK_ARG(B > 0 && Hi % 4 == 0 && Wi % 4 == 0, "patchify_cat: bad shape B=%d Hi=%d Wi=%d", B, Hi, Wi);
@@ -784,11 +801,11 @@ extern "C" int swinb200_patchify_cat(int n_src, const float* const* srcs, const 
   if (act_dtype == SWINB200_BF16) {
     const size_t smem = (size_t)kPatchTok * (C * 16 + 8) * 2;
     SWB_CUDA(cudaFuncSetAttribute(patchify_cat_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    patchify_cat_kernel<__nv_bfloat16><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, (__nv_bfloat16*)out, B, C, Hi, Wi, ntok);
+    patchify_cat_kernel<__nv_bfloat16><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, mean, stdv, (__nv_bfloat16*)out, B, C, Hi, Wi, ntok);
   } else if (act_dtype == SWINB200_F32) {
     const size_t smem = (size_t)kPatchTok * (C * 16 + 8) * 4;
     SWB_CUDA(cudaFuncSetAttribute(patchify_cat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    patchify_cat_kernel<float><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, (float*)out, B, C, Hi, Wi, ntok);
+    patchify_cat_kernel<float><<<blocks, 256, smem, (cudaStream_t)stream>>>(ps, mean, stdv, (float*)out, B, C, Hi, Wi, ntok);
   } else {
     SWB_CHECK_ARG(false, "patchify_cat: bad act_dtype %d", act_dtype);
   }
@@ -797,18 +814,18 @@ extern "C" int swinb200_patchify_cat(int n_src, const float* const* srcs, const 
 }
 
 template <typename T>
-static int launch_unpatchify(const T* y, const float* skip, int skip_chans, float* out, int B, int Co, int Hi, int Wi, int order,
-                             cudaStream_t s) {
+static int launch_unpatchify(const T* y, const float* skip, int skip_chans, const float* smean, const float* sstd, float* out, int B,
+                             int Co, int Hi, int Wi, int order, cudaStream_t s) {
   const int ntok = B * (Hi / 4) * (Wi / 4);
   const int K = Co * 16;
   const size_t smem = (size_t)kPatchTok * (K + 8) * sizeof(T);
   const int blocks = (ntok + kPatchTok - 1) / kPatchTok;
   if (order == 1) {
     SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unpatchify_kernel<T, 1><<<blocks, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+    unpatchify_kernel<T, 1><<<blocks, 256, smem, s>>>(y, skip, skip_chans, smean, sstd, out, B, Co, Hi, Wi, ntok);
   } else {
     SWB_CUDA(cudaFuncSetAttribute(unpatchify_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unpatchify_kernel<T, 0><<<blocks, 256, smem, s>>>(y, skip, skip_chans, out, B, Co, Hi, Wi, ntok);
+    unpatchify_kernel<T, 0><<<blocks, 256, smem, s>>>(y, skip, skip_chans, smean, sstd, out, B, Co, Hi, Wi, ntok);
   }
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
@@ -816,14 +833,22 @@ static int launch_unpatchify(const T* y, const float* skip, int skip_chans, floa
 
 extern "C" int swinb200_unpatchify(const void* y, int act_dtype, const float* skip, int skip_chans, float* out, int B, int Co,
                                    int Hi, int Wi, int P, int order, void* stream) {
+  return swinb200_unpatchify_norm(y, act_dtype, skip, skip_chans, nullptr, nullptr, out, B, Co, Hi, Wi, P, order, stream);
+}
+
+extern "C" int swinb200_unpatchify_norm(const void* y, int act_dtype, const float* skip, int skip_chans, const float* skip_mean,
+                                        const float* skip_std, float* out, int B, int Co, int Hi, int Wi, int P, int order,
+                                        void* stream) {
+  SWB_CHECK_ARG((skip_mean == nullptr) == (skip_std == nullptr), "unpatchify: skip mean and std must be given together");
+  SWB_CHECK_ARG(skip_mean == nullptr || skip != nullptr, "unpatchify: skip statistics without a skip tensor");
   SWB_CHECK_ARG(order == 0 || order == 1, "unpatchify: order must be 0 or 1");
   SWB_CHECK_ARG(y && out, "unpatchify: null pointer");
   SWB_CHECK_ARG(P == 4, "unpatchify: only patch_size 4 is supported (got %d)", P);
   SWB_CHECK_ARG(B > 0 && Co > 0 && Hi % 4 == 0 && Wi % 4 == 0, "unpatchify: bad shape");
   SWB_CHECK_ARG(skip == nullptr || skip_chans >= Co, "unpatchify: skip has fewer channels (%d) than the output (%d)", skip_chans, Co);
   SWB_CHECK_ARG((size_t)kPatchTok * (Co * 16 + 8) * 4 <= 220 * 1024, "unpatchify: Co=%d too large", Co);
-  if (act_dtype == SWINB200_BF16) return launch_unpatchify<__nv_bfloat16>((const __nv_bfloat16*)y, skip, skip_chans, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
-  if (act_dtype == SWINB200_F32) return launch_unpatchify<float>((const float*)y, skip, skip_chans, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_BF16) return launch_unpatchify<__nv_bfloat16>((const __nv_bfloat16*)y, skip, skip_chans, skip_mean, skip_std, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
+  if (act_dtype == SWINB200_F32) return launch_unpatchify<float>((const float*)y, skip, skip_chans, skip_mean, skip_std, out, B, Co, Hi, Wi, order, (cudaStream_t)stream);
   SWB_CHECK_ARG(false, "unpatchify: bad act_dtype %d", act_dtype);
 }
 

@@ -82,7 +82,9 @@ __device__ __forceinline__ float normal_cdf_fast(float x) {
   p = fmaf(p, u, 0.3988475203514099f);
   return fmaf(xc, p, 0.5f);
 }
-__device__ __forceinline__ float gelu_fast(float x) { return x * normal_cdf_fast(x); }
+// The multiplier is max(x, -4), not x: below the clamp Phi_fast stays at Phi(-4) = 3.2e-5 instead of decaying, and x * Phi_fast
+// would grow linearly with |x|; max(x, -4) * Phi_fast(-4) = -1.3e-4 bounds the tail error (the exact value tends to 0-).
+__device__ __forceinline__ float gelu_fast(float x) { return fmaxf(x, -4.0f) * normal_cdf_fast(x); }
 
 // Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction, operands in 64-bit register
 // pairs).  The epilogues are issue-slot bound, so evaluating the polynomial two columns at a time halves their cost.
@@ -108,7 +110,7 @@ __device__ __forceinline__ f32x2 normal_cdf_fast2(float x0, float x1) {
   return fma2(xc, q, splat2(0.5f));
 }
 __device__ __forceinline__ void gelu_fast2(float x0, float x1, float& g0, float& g1) {
-  unpack2(mul2(pack2(x0, x1), normal_cdf_fast2(x0, x1)), g0, g1);
+  unpack2(mul2(pack2(fmaxf(x0, -4.0f), fmaxf(x1, -4.0f)), normal_cdf_fast2(x0, x1)), g0, g1);
 }
 // v{0,1} *= d/dx[x Phi(x)] at h{0,1}
 __device__ __forceinline__ void gelu_grad_mul2(float h0, float h1, float& v0, float& v1) {

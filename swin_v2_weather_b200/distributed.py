@@ -27,9 +27,6 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-            # NCCL prints its version banner on stdout at INFO/VERSION level; keep stdout for results only
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SWINB200_KEEP_NCCL_DEBUG"):
-                os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend=backend, init_method="env://", rank=rank, world_size=world)
     return rank, world, local
 
@@ -42,7 +39,10 @@ def local_batch_size(global_batch: int, world: int) -> int:
 
 
 def shard_indices(n_samples: int, rank: int, world: int):
-    """Contiguous per-rank shard of a sample index range (deterministic, no overlap, covers everything)."""
+    """Contiguous per-rank shard of a sample index range (deterministic, no overlap, covers everything; an uneven split
+    is rejected like `local_batch_size` does, reference train.py:147-148)."""
+    if n_samples % world != 0:
+        raise ValueError(f"{n_samples} samples are not divisible by world size {world}")
     per = n_samples // world
     return range(rank * per, (rank + 1) * per)
 

@@ -35,7 +35,7 @@ class _ShadowCache:
             return ent[3]
         reuse = ent is not None and ent[0]() is w and ent[3].shape == w.shape and ent[3].device == w.device
         sh = ops.cast_bf16(w.detach().contiguous(), ent[3] if reuse else None)
-        if len(self._store) > 4096:
+        if ent is None:     # a new parameter: drop the shadows of parameters that have been freed since (discarded models)
             self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
         self._store[key] = (weakref.ref(w), ver, ptr, sh)
         return sh
@@ -70,16 +70,19 @@ class PatchEmbedFn(torch.autograd.Function):
     Returns the fp32 token stream (B, H, W, C) and its activation-type shadow."""
 
     @staticmethod
-    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode, *more_channels):
+    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b, pos_embed, patch: int, mode: ComputeMode, in_mean, in_std, *more_channels):
         """`more_channels`: further (B or 1, C_s, Hi, Wi) tensors whose channels follow those of `img` (zenith angle, static
-        land-mask / orography features): the im2col reads all of them in place, torch.cat never runs."""
+        land-mask / orography features): the im2col reads all of them in place, torch.cat never runs.
+        `in_mean` / `in_std`: optional (Cin,) per-channel statistics; the im2col then reads (x - mean) / std -- the loaders'
+        z-score (data_loader_era5_dali.py:77-90) without a normalised copy of the field."""
         ctx.set_materialize_grads(False)   # no zero-filled gradient for the (non-differentiable) bf16 shadow output
         B, C0, Hi, Wi = img.shape
         Cin = C0 + sum(t.shape[1] for t in more_channels)
         E = proj_w.shape[0]
         H, W = Hi // patch, Wi // patch
-        if more_channels:
-            patches = ops.patchify_cat([img.contiguous()] + [t.detach().float().contiguous() for t in more_channels], patch, mode)
+        if more_channels or in_mean is not None:
+            patches = ops.patchify_cat([img.contiguous()] + [t.detach().float().contiguous() for t in more_channels], patch, mode,
+                                       in_mean, in_std)
         else:
             patches = ops.patchify(img.contiguous(), patch, 0, mode)                   # (T, Cin*P*P)
         w2 = SHADOWS.get(proj_w, mode).reshape(E, -1)
@@ -92,6 +95,7 @@ class PatchEmbedFn(torch.autograd.Function):
         x, xb, stats = ops.ln_residual_fwd(z0, None, norm_w.detach(), norm_b.detach(), None, pos_tok, H * W, mode)
         ctx.save_for_backward(patches, z0, stats, norm_w, proj_w)
         ctx.meta = (B, C0, Cin, Hi, Wi, E, H, W, patch, mode, pos_embed is not None, tuple(proj_w.shape), len(more_channels))
+        ctx.in_std = in_std
         shadow = xb if mode.act_dtype != torch.float32 else x.new_empty(0)   # fp32 mode: the stream is its own shadow
         ctx.mark_non_differentiable(shadow)
         return x.view(B, H, W, E), shadow
@@ -116,7 +120,9 @@ class PatchEmbedFn(torch.autograd.Function):
                 w2 = w2[:, :C0 * patch * patch].contiguous()
             dpatch = ops.gemm(mode, dz0, 0, w2, 1, EPI_BIAS)                          # (T, C0*P*P), columns (c, p, q)
             dimg = ops.unpatchify(dpatch, None, B, C0, Hi, Wi, patch, order=0)
-        return (dimg, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None) + (None,) * n_more
+            if ctx.in_std is not None:      # d/dx (x - m)/s = 1/s
+                dimg = dimg / ctx.in_std[:C0].view(1, C0, 1, 1)
+        return (dimg, dw.view(wshape), dbias, dgamma, dbeta, dpos, None, None, None, None) + (None,) * n_more
 
 
 # ---- one SwinV2 block ------------------------------------------------------------------------------------
@@ -212,14 +218,16 @@ class HeadFn(torch.autograd.Function):
     """reference: forward_head + `x + skip[:, :out_chans]` (swinv2_global.py:784-803)."""
 
     @staticmethod
-    def forward(ctx, x, xb, head_w, skip, out_chans: int, patch: int, mode: ComputeMode):
+    def forward(ctx, x, xb, head_w, skip, out_chans: int, patch: int, mode: ComputeMode, skip_mean=None, skip_std=None):
         B, H, W, C = x.shape
         if mode.act_dtype == torch.float32:
             xb = x.contiguous().view(B * H * W, C)
         wh = SHADOWS.get(head_w, mode)
         y = ops.gemm(mode, xb, 0, wh, 0, EPI_BIAS)                                               # (T, P*P*Co), cols (p,q,c)
-        out = ops.unpatchify(y, None if skip is None else skip.contiguous(), B, out_chans, H * patch, W * patch, patch)
+        out = ops.unpatchify(y, None if skip is None else skip.contiguous(), B, out_chans, H * patch, W * patch, patch,
+                             skip_mean=skip_mean, skip_std=skip_std)
         ctx.save_for_backward(xb, head_w)
+        ctx.skip_std = skip_std
         ctx.meta = (B, H, W, C, out_chans, patch, mode, skip is not None, None if skip is None else skip.shape[1])
         return out
 
@@ -237,8 +245,8 @@ class HeadFn(torch.autograd.Function):
         dskip = None
         if has_skip and ctx.needs_input_grad[3]:
             dskip = torch.zeros((B, skip_ch, H * patch, W * patch), dtype=torch.float32, device=dout.device)
-            dskip[:, :Co] = dout
-        return dx.view(B, H, W, C), None, dw, dskip, None, None, None
+            dskip[:, :Co] = dout if ctx.skip_std is None else dout / ctx.skip_std[:Co].view(1, Co, 1, 1)
+        return dx.view(B, H, W, C), None, dw, dskip, None, None, None, None, None
 
 
 # ---- loss ---------------------------------------------------------------------------------------------------------
@@ -260,3 +268,21 @@ class LatWeightedL2Fn(torch.autograd.Function):
         g = gloss.detach().to(torch.float32).reshape(1).contiguous()
         dprd = ops.latw_l2_bwd(prd, tar, qw, chw, num, den, g, *ctx.flags)
         return dprd, None, None, None, None, None
+
+
+class LatWeightedL1Fn(torch.autograd.Function):
+    """reference: GeometricLpLoss.rel / .abs with p=1 (utils/losses.py:116-124, 188-232)."""
+
+    @staticmethod
+    def forward(ctx, prd, tar, qw, chw, relative: bool):
+        prd, tar = prd.contiguous(), tar.contiguous()
+        loss, sums = ops.latw_l1_fwd(prd, tar, qw, chw, relative)
+        ctx.save_for_backward(prd, tar, qw, chw, sums)
+        ctx.relative = relative
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gloss):
+        prd, tar, qw, chw, sums = ctx.saved_tensors
+        g = gloss.detach().to(torch.float32).reshape(1).contiguous()
+        return ops.latw_l1_bwd(prd, tar, qw, chw, sums, g, ctx.relative), None, None, None, None

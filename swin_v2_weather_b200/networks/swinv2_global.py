@@ -388,6 +388,13 @@ class SwinTransformerV2Cr(nn.Module):
         window_size = tuple([s // img_window_ratio for s in img_size]) if window_size is None else to_2tuple(window_size)
         if patch_size != 4:
             raise NotImplementedError("the kernels are specialised for patch_size 4 (every reference config)")
+        # kernel limits, checked here rather than at the first forward: the LayerNorm kernels hold a row in registers
+        # (C <= 1024) and the attention kernels are instantiated for head_dim <= 192.  The one shipped config beyond them is
+        # swin_73var_geo_depth24_e2048_mlp2_chweight_invar (embed_dim 2048, head_dim 256) -- see DESIGN.md section 7.
+        if embed_dim > 1024 or embed_dim % 8 != 0:
+            raise NotImplementedError(f"embed_dim {embed_dim}: the B200 kernels support multiples of 8 up to 1024")
+        if embed_dim % num_heads[0] != 0 or (embed_dim // num_heads[0]) % 8 != 0 or embed_dim // num_heads[0] > 192:
+            raise NotImplementedError(f"head_dim {embed_dim / num_heads[0]:g}: the attention kernels support multiples of 8 up to 192")
         self.patch_size = patch_size
         self.img_size = img_size
         self.window_size = window_size
@@ -430,30 +437,48 @@ class SwinTransformerV2Cr(nn.Module):
         return self
 
     # -- forward ------------------------------------------------------------------------------------------
-    def forward_features(self, x) -> torch.Tensor:
+    def _input_stats(self, input_stats, n_chans: int, device):
+        """(mean, std) given for the leading channels of the input -> full-length fp32 device vectors (mean 0 / std 1 for the
+        channels that pass through unchanged: zenith angle, land mask, orography)."""
+        if input_stats is None:
+            return None, None
+        mean, std = (torch.as_tensor(t, dtype=torch.float32).reshape(-1).to(device) for t in input_stats)
+        if mean.numel() != std.numel() or mean.numel() > n_chans:
+            raise ValueError(f"input_stats: {mean.numel()} means / {std.numel()} stds for an input of {n_chans} channels")
+        pad = n_chans - mean.numel()
+        if pad:
+            mean = torch.cat([mean, mean.new_zeros(pad)])
+            std = torch.cat([std, std.new_ones(pad)])
+        return mean.contiguous(), std.contiguous()
+
+    def forward_features(self, x, input_stats=None) -> torch.Tensor:
         """x: (B, Cin, H, W), or a tuple / list of channel groups [(B, C0, H, W), (B or 1, C1, H, W), ...] standing for their
-        concatenation along dim 1 (what PreProcessor / MultiStepWrapper would otherwise build with torch.cat)."""
+        concatenation along dim 1 (what PreProcessor / MultiStepWrapper would otherwise build with torch.cat).
+        `input_stats` = (mean, std) per channel of a RAW field: the z-score the reference's loaders apply before the model
+        (utils/data_loader_era5_dali.py:77-90) then happens inside the PatchEmbed im2col."""
         mode = ops.MODES[self.compute_mode]
         parts = [t.float() for t in x] if isinstance(x, (tuple, list)) else [x.float()]
         B, _, H, W = parts[0].shape
         assert H == self.img_size[0], f"Input image height ({H}) doesn't match model ({self.img_size[0]})."
         assert W == self.img_size[1], f"Input image width ({W}) doesn't match model ({self.img_size[1]})."
         pe = self.patch_embed
+        mean, std = self._input_stats(input_stats, sum(t.shape[1] for t in parts), parts[0].device)
         tok, shadow = Fn.PatchEmbedFn.apply(parts[0], pe.proj.weight, pe.proj.bias, pe.norm.weight, pe.norm.bias,
-                                            self.pos_embed if self.full_pos_embed else None, self.patch_size, mode, *parts[1:])
+                                            self.pos_embed if self.full_pos_embed else None, self.patch_size, mode, mean, std,
+                                            *parts[1:])
         x = _carry_shadow(bhwc_to_bchw(tok), shadow)
         return self.stages(x)
 
-    def forward_head(self, x: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_head(self, x: torch.Tensor, skip: Optional[torch.Tensor] = None, skip_stats=(None, None)) -> torch.Tensor:
         mode = ops.MODES[self.compute_mode]
         shadow = getattr(x, _SHADOW_ATTR, None)
         t = bchw_to_bhwc(x)
         if not t.is_contiguous():
             t = t.contiguous()
         t = _carry_shadow(t.float(), shadow)
-        return Fn.HeadFn.apply(t, _shadow_of(t, mode), self.head.weight, skip, self.out_chans, self.patch_size, mode)
+        return Fn.HeadFn.apply(t, _shadow_of(t, mode), self.head.weight, skip, self.out_chans, self.patch_size, mode, *skip_stats)
 
-    def forward(self, x) -> torch.Tensor:
+    def forward(self, x, input_stats=None) -> torch.Tensor:
         if isinstance(x, (tuple, list)):
             x = [t.float() for t in x]
             if self.residual and x[0].shape[1] < self.out_chans:      # the skip needs the first out_chans channels in one tensor
@@ -462,8 +487,12 @@ class SwinTransformerV2Cr(nn.Module):
             x = x.float()
         first = x[0] if isinstance(x, list) else x
         skip = first if self.residual else None   # the reference adds zeros_like(x) otherwise (:795-802); adding 0 is skipped
-        feats = self.forward_features(x)
-        return self.forward_head(feats, skip)
+        feats = self.forward_features(x, input_stats)
+        skip_stats = (None, None)
+        if skip is not None and input_stats is not None:
+            n_in = sum(t.shape[1] for t in x) if isinstance(x, list) else x.shape[1]
+            skip_stats = tuple(t[:skip.shape[1]].contiguous() for t in self._input_stats(input_stats, n_in, skip.device))
+        return self.forward_head(feats, skip, skip_stats)
 
     # -- reference API odds and ends ----------------------------------------------------------------------------
     def update_input_size(self, new_img_size=None, new_window_size=None, img_window_ratio: int = 32) -> None:

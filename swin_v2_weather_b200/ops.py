@@ -90,9 +90,11 @@ def patchify(img: torch.Tensor, patch: int, order: int, mode: ComputeMode) -> to
     return out
 
 
-def patchify_cat(parts, patch: int, mode: ComputeMode) -> torch.Tensor:
+def patchify_cat(parts, patch: int, mode: ComputeMode, mean: Optional[torch.Tensor] = None,
+                 std: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Order-0 im2col of the channel-wise concatenation of `parts` without materialising it.  Every part is a contiguous
-    fp32 (B or 1, C_s, Hi, Wi) CUDA tensor; a leading dimension of 1 is shared by the whole batch (static features)."""
+    fp32 (B or 1, C_s, Hi, Wi) CUDA tensor; a leading dimension of 1 is shared by the whole batch (static features).
+    `mean` / `std`: optional (C,) fp32 per-channel statistics -- values enter the im2col as (x - mean) / std."""
     import ctypes
     B = max(p.shape[0] for p in parts)
     Hi, Wi = parts[0].shape[-2:]
@@ -106,16 +108,22 @@ def patchify_cat(parts, patch: int, mode: ComputeMode) -> torch.Tensor:
     n, C = len(parts), sum(chans)
     T = B * (Hi // patch) * (Wi // patch)
     out = torch.empty((T, C * patch * patch), dtype=mode.act_dtype, device=parts[0].device)
-    _lib.call("swinb200_patchify_cat", n, (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int * n)(*chans), (ctypes.c_longlong * n)(*strides),
-              out.data_ptr(), mode.act_code, B, Hi, Wi, patch, _stream())
+    if mean is not None and (mean.numel() != C or std is None or std.numel() != C):
+        raise SwinB200Error(f"patchify_cat: mean / std must have {C} entries")
+    _lib.call("swinb200_patchify_cat_norm", n, (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int * n)(*chans), (ctypes.c_longlong * n)(*strides),
+              _chk(mean, "mean", torch.float32, True), _chk(std, "std", torch.float32, True), out.data_ptr(), mode.act_code, B, Hi, Wi,
+              patch, _stream())
     return out
 
 
 def unpatchify(y: torch.Tensor, skip: Optional[torch.Tensor], B: int, Co: int, Hi: int, Wi: int, patch: int,
-               order: int = 1) -> torch.Tensor:
+               order: int = 1, skip_mean: Optional[torch.Tensor] = None, skip_std: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty((B, Co, Hi, Wi), dtype=torch.float32, device=y.device)
     skip_ch = 0 if skip is None else skip.shape[1]
-    _lib.call("swinb200_unpatchify", _chk(y, "y"), _code(y.dtype), _chk(skip, "skip", torch.float32, True), skip_ch, out.data_ptr(),
+    if skip_mean is not None and (skip_mean.numel() < Co or skip_std is None or skip_std.numel() < Co):
+        raise SwinB200Error(f"unpatchify: skip mean / std need at least {Co} entries")
+    _lib.call("swinb200_unpatchify_norm", _chk(y, "y"), _code(y.dtype), _chk(skip, "skip", torch.float32, True), skip_ch,
+              _chk(skip_mean, "skip_mean", torch.float32, True), _chk(skip_std, "skip_std", torch.float32, True), out.data_ptr(),
               B, Co, Hi, Wi, patch, order, _stream())
     return out
 
@@ -292,6 +300,7 @@ def window_attn_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, B, H, W, C, heads, 
 
 # ---- loss ---------------------------------------------------------------------------------------------------
 def latw_l2_fwd(prd, tar, qw, chw, relative: bool, squared: bool = True):
+    _check_loss_args(prd, tar, qw, chw)
     B, C, H, W = prd.shape
     num = torch.empty((B * C,), dtype=torch.float32, device=prd.device)
     den = torch.empty((B * C,), dtype=torch.float32, device=prd.device)
@@ -302,9 +311,50 @@ def latw_l2_fwd(prd, tar, qw, chw, relative: bool, squared: bool = True):
 
 
 def latw_l2_bwd(prd, tar, qw, chw, num, den, gloss, relative: bool, squared: bool = True):
+    _check_loss_args(prd, tar, qw, chw)
     B, C, H, W = prd.shape
     dprd = torch.empty_like(prd)
     _lib.call("swinb200_latw_l2_bwd", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
               _chk(chw, "chw", torch.float32), _chk(num, "num", torch.float32), _chk(den, "den", torch.float32),
               _chk(gloss, "gloss", torch.float32), int(relative), int(squared), dprd.data_ptr(), B, C, H, W, _stream())
     return dprd
+
+
+def _check_loss_args(prd, tar, qw, chw=None):
+    if prd.dim() != 4 or prd.shape != tar.shape:
+        raise SwinB200Error(f"loss: prediction {tuple(prd.shape)} and target {tuple(tar.shape)} must be equal (B, C, H, W) shapes")
+    if qw.numel() != prd.shape[2]:
+        raise SwinB200Error(f"loss: {qw.numel()} quadrature row weights for {prd.shape[2]} rows")
+    if chw is not None and chw.numel() != prd.shape[1]:
+        raise SwinB200Error(f"loss: {chw.numel()} channel weights for {prd.shape[1]} channels")
+
+
+def latw_l1_fwd(prd, tar, qw, chw, relative: bool):
+    _check_loss_args(prd, tar, qw, chw)
+    B, C, H, W = prd.shape
+    sums = torch.empty((B * C, 2), dtype=torch.float32, device=prd.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=prd.device)
+    _lib.call("swinb200_latw_l1_fwd", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
+              _chk(chw, "chw", torch.float32), int(relative), sums.data_ptr(), loss.data_ptr(), B, C, H, W, _stream())
+    return loss, sums
+
+
+def latw_l1_bwd(prd, tar, qw, chw, sums, gloss, relative: bool):
+    _check_loss_args(prd, tar, qw, chw)
+    B, C, H, W = prd.shape
+    dprd = torch.empty_like(prd)
+    _lib.call("swinb200_latw_l1_bwd", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
+              _chk(chw, "chw", torch.float32), _chk(sums, "sums", torch.float32), _chk(gloss, "gloss", torch.float32), int(relative),
+              dprd.data_ptr(), B, C, H, W, _stream())
+    return dprd
+
+
+def latw_acc(prd, tar, qw):
+    """(B, C) anomaly correlation sum(q p t) / sqrt(sum(q p p) sum(q t t)) in one pass over prd and tar."""
+    _check_loss_args(prd, tar, qw)
+    B, C, H, W = prd.shape
+    sums = torch.empty((B * C, 3), dtype=torch.float32, device=prd.device)
+    acc = torch.empty((B, C), dtype=torch.float32, device=prd.device)
+    _lib.call("swinb200_latw_acc", _chk(prd, "prd", torch.float32), _chk(tar, "tar", torch.float32), _chk(qw, "qw", torch.float32),
+              sums.data_ptr(), acc.data_ptr(), B, C, H, W, _stream())
+    return acc

@@ -17,8 +17,6 @@ class GridQuadrature(nn.Module):
             raise NotImplementedError(
                 f"quadrature rule {quadrature_rule!r}: only 'naive' (equiangular grid) is on the hot path; "
                 "clenshaw-curtiss / legendre-gauss need torch_harmonics and are not used by any shipped config")
-        if pole_mask:
-            raise NotImplementedError("pole-masked losses hit an undefined name in the reference (utils/grids.py:99)")
         nlat, nlon = int(img_shape[0]), int(img_shape[1])
         jacobian = torch.clamp(torch.sin(torch.linspace(0, torch.pi, nlat)), min=0.)
         dA = (2 * torch.pi / nlon) * (torch.pi / nlat)
@@ -26,6 +24,11 @@ class GridQuadrature(nn.Module):
         w = w * (4. * torch.pi) / torch.sum(w)
         if normalize:
             w = w / (4. * torch.pi)
+        if (pole_mask is not None) and (pole_mask > 0):
+            # reference utils/grids.py:96-99 zeroes the rows next to both poles; upstream indexes an undefined `sizes`
+            # there (NameError on any 'pole-masked' loss) -- the evident intent, `img_shape[0]`, is what runs here
+            w[:pole_mask, :] = 0.
+            w[nlat - pole_mask:, :] = 0.
         if crop_shape is not None:
             w = w[crop_offset[0]:crop_offset[0] + crop_shape[0], crop_offset[1]:crop_offset[1] + crop_shape[1]]
         self.shape = tuple(w.shape)

@@ -4,8 +4,9 @@ multistep weighting follow the reference; what is computed on the GPU is
 
     sum_{b,c} chw_c * f( I[(p-t)^2] / I[t^2] )   (relative)    or    sum_{b,c} chw_c * f( I[(p-t)^2] )   (absolute)
 
-with I[x] = sum_{h,w} x * q_h and f = identity ('squared') or sqrt.  L1, H1 and pole-masked variants are not on
-the hot path of any shipped config and raise NotImplementedError.
+with I[x] = sum_{h,w} x * q_h and f = identity ('squared') or sqrt; the 'l1' family (utils/losses.py:116-124) is the
+same reduction over |p-t| (and |t|), and 'pole-masked' zeroes the quadrature rows next to the poles.  The spectral H1
+loss needs torch_harmonics and is not part of the path.
 """
 from __future__ import annotations
 
@@ -15,20 +16,20 @@ import numpy as np
 import torch
 from torch import nn
 
-from ..functional import LatWeightedL2Fn
+from ..functional import LatWeightedL1Fn, LatWeightedL2Fn
 from .grids import GridQuadrature
 
 
 class GeometricLpLoss(nn.Module):
-    """reference: utils/losses.py:154-240 (p = 2 only)."""
+    """reference: utils/losses.py:154-240 (p in {1, 2})."""
 
     def __init__(self, img_shape: Tuple[int, int], crop_shape: Tuple[int, int], crop_offset: Tuple[int, int],
                  p: Optional[float] = 2., size_average: Optional[bool] = False, reduction: Optional[bool] = True,
                  absolute: Optional[bool] = False, squared: Optional[bool] = False, pole_mask: Optional[int] = 0,
                  jacobian: Optional[str] = 's2', quadrature_rule: Optional[str] = 'naive'):
         super().__init__()
-        if p != 2:
-            raise NotImplementedError("only the L2 losses are on the hot path")
+        if p not in (1, 2):
+            raise NotImplementedError("GeometricLpLoss: p must be 1 or 2 (the only values LossHandler ever passes)")
         if size_average or not reduction:
             raise NotImplementedError("size_average / reduction=False are never used by the reference's LossHandler")
         self.p = p
@@ -48,8 +49,14 @@ class GeometricLpLoss(nn.Module):
         chw = chw.reshape(-1).to(device=prd.device, dtype=torch.float32)
         if chw.numel() != C:
             raise ValueError(f"channel weights have {chw.numel()} entries for {C} channels")
-        return LatWeightedL2Fn.apply(prd.float(), tar.float(), self.quadrature.quad_row_weight, chw.contiguous(),
-                                     relative, bool(self.squared))
+        if prd.shape != tar.shape:
+            raise ValueError(f"prediction {tuple(prd.shape)} and target {tuple(tar.shape)} shapes differ")
+        qw = self.quadrature.quad_row_weight
+        if qw.numel() != prd.shape[2]:
+            raise ValueError(f"quadrature has {qw.numel()} rows, the prediction {prd.shape[2]}")
+        if self.p == 1:   # |x|^(1/1): `squared` has no effect (utils/losses.py:195-196, 218-219)
+            return LatWeightedL1Fn.apply(prd.float(), tar.float(), qw, chw.contiguous(), relative)
+        return LatWeightedL2Fn.apply(prd.float(), tar.float(), qw, chw.contiguous(), relative, bool(self.squared))
 
     def abs(self, prd, tar, chw):
         return self._run(prd, tar, chw, False)
@@ -115,8 +122,12 @@ class LossHandler(nn.Module):
                 # the reference passes jacobian='flat' here but GeometricLpLoss ignores it (utils/losses.py:113-114,168)
                 self.loss_obj = GeometricLpLoss(self.img_shape, self.crop_shape, self.crop_offset, p=2, absolute=absolute,
                                                 pole_mask=pole_mask, jacobian='flat')
-        elif 'l1' in loss_type or 'geometric h1' in self.loss_type:
-            raise NotImplementedError(f"loss {self.loss_type!r} is not on the B200 hot path (L2 family only)")
+        elif 'l1' in loss_type:
+            self.loss_obj = GeometricLpLoss(self.img_shape, self.crop_shape, self.crop_offset, p=1, absolute=absolute,
+                                            pole_mask=pole_mask,
+                                            **(dict(quadrature_rule=quadrature_rule_type) if 'geometric' in loss_type else dict(jacobian='flat')))
+        elif 'geometric h1' in self.loss_type:
+            raise NotImplementedError("the spectral H1 loss needs torch_harmonics' RealSHT; it is not on the B200 hot path")
         else:
             raise ValueError(f"Unknown loss function: {self.loss_type}")
 

@@ -1,5 +1,5 @@
-"""Latitude-weighted RMSE of the validation loop (reference utils/weighted_acc_rmse.py:51-87, train.py:305-351), SURVEY 8(f)
-rank 4: the same bandwidth-bound weighted reduction as the training loss, so it runs on the loss kernel
+"""Latitude-weighted RMSE and anomaly correlation of the validation loop (reference utils/weighted_acc_rmse.py:51-105,
+train.py:305-351), SURVEY 8(f) rank 4: the same bandwidth-bound weighted reduction as the training loss, so it runs on the loss kernel
 (`swinb200_latw_l2_fwd`: num[b, c] = sum_hw qw[h] (p - t)^2) with the reference's own row weights
 
     w[h] = num_lat * cos(3.1416/180 * lat(h)) / sum_h cos(3.1416/180 * lat(h)),   lat(h) = 90 - h * 180/(num_lat - 1)
@@ -42,3 +42,19 @@ def weighted_rmse_torch_channels(pred: torch.Tensor, target: torch.Tensor) -> to
 
 def weighted_rmse_torch(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return torch.mean(weighted_rmse_torch_channels(pred, target), dim=0)
+
+
+def weighted_acc_torch_channels(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """(n, c, h, w) x 2 -> latitude-weighted anomaly correlation per sample and channel, (n, c)  (reference :89-99):
+    sum(w p t) / sqrt(sum(w p p) * sum(w t t)) from one fused three-accumulator pass (`swinb200_latw_acc`)."""
+    if pred.shape != target.shape or pred.dim() != 4:
+        raise ValueError(f"weighted_acc: expected two (n, c, h, w) tensors, got {tuple(pred.shape)} and {tuple(target.shape)}")
+    n, c, h, w = pred.shape
+    lat_t = torch.arange(start=0, end=h, device=pred.device)
+    s = torch.sum(torch.cos(3.1416 / 180. * lat(lat_t, h)))
+    qw = latitude_weighting_factor_torch(lat_t, h, s).to(torch.float32).contiguous()
+    return ops.latw_acc(pred.detach().float().contiguous(), target.detach().float().contiguous(), qw)
+
+
+def weighted_acc_torch(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    return torch.mean(weighted_acc_torch_channels(pred, target), dim=0)

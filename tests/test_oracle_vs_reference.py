@@ -78,3 +78,58 @@ def test_quadrature_and_loss_handler_weights():
     assert torch.equal(ref.channel_weights, mine.channel_weights)
     assert torch.equal(ref.loss_obj.quadrature.quad_weight, mine.loss_obj.quadrature.quad_weight.contiguous())
     assert torch.equal(ref.multistep_weight, mine.multistep_weight)
+
+
+def _load_ref_metrics():
+    import importlib.util
+    import os
+    import sys
+    name = "_ref_weighted_acc_rmse"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(shim.REFERENCE_ROOT, "utils", "weighted_acc_rmse.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("loss", ["weighted absolute temp-std squared geometric l2", "weighted temp-std geometric l2",
+                                  "weighted geometric l1", "absolute geometric l1", "l2", "absolute squared geometric l2"])
+def test_loss_handler_variants_match_reference(loss, tmp_path):
+    """Config-4 channel weights (`'auto'` table x temp-std ratio, utils/losses.py:56-99) and the L1 / non-squared loss
+    variants (:101-124): oracle restatement vs the live reference LossHandler -- weights bit-exact, loss and dL/dprd 1e-6."""
+    import numpy as np
+    from types import SimpleNamespace
+    _, losses = shim.import_reference()
+    C = 73
+    rng = np.random.default_rng(7)
+    gstd = np.ones((1, C, 1, 1), dtype=np.float32)
+    tstd = rng.uniform(0.2, 1.0, size=(1, C, 1, 1)).astype(np.float32)
+    np.save(tmp_path / "global_stds.npy", gstd)
+    np.save(tmp_path / "time_diff_stds.npy", tstd)
+    p = SimpleNamespace(n_future=0, img_shape_x=36, img_shape_y=72, loss=loss, channel_weights='auto', n_out_channels=C,
+                        channel_names=list(O.CHANNEL_NAMES_73), out_channels=list(range(C)), dt=1, model_grid_type='equiangular',
+                        global_stds_path=str(tmp_path / "global_stds.npy"), time_diff_stds_path=str(tmp_path / "time_diff_stds.npy"))
+    ref = losses.LossHandler(p).train()
+    w = O.loss_handler_channel_weights(loss, 'auto', p.channel_names, C, p.out_channels, 1, gstd, tstd)
+    assert torch.equal(ref.channel_weights.reshape(-1).float(), w)
+    g = torch.Generator().manual_seed(2)
+    prd = torch.randn(2, C, 36, 72, generator=g, requires_grad=True)
+    tar = torch.randn(2, C, 36, 72, generator=g)
+    l_ref = ref(prd, tar, None)
+    g_ref, = torch.autograd.grad(l_ref, prd)
+    prd2 = prd.detach().clone().requires_grad_(True)
+    l_or = O.loss_handler(prd2, tar, loss, w, n_future=0, training=True)
+    g_or, = torch.autograd.grad(l_or, prd2)
+    assert abs(float(l_or) - float(l_ref)) <= 1e-6 * abs(float(l_ref))
+    assert O.rel_l2(g_or, g_ref) < 1e-6
+
+
+def test_validation_metrics_and_zscore_match_reference():
+    m = _load_ref_metrics()
+    g = torch.Generator().manual_seed(3)
+    pred = torch.randn(3, 5, 37, 72, generator=g)
+    tar = torch.randn(3, 5, 37, 72, generator=g)
+    assert torch.allclose(O.weighted_rmse_channels(pred, tar), m.weighted_rmse_torch_channels(pred, tar), rtol=1e-6, atol=0)
+    assert torch.allclose(O.weighted_acc_channels(pred, tar), m.weighted_acc_torch_channels(pred, tar), rtol=1e-5, atol=1e-7)

@@ -1,0 +1,238 @@
+"""Parity of the CUDA path against the oracle ON THE CONFIGURATIONS THE BENCHMARK RUNS:
+
+  (a) headline width / heads / depth -- C = 768, 8 heads (head_dim 96), depth 12, 73 -> 73 channels -- on a 72 x 144 image
+      (same 9 x 18 windows, 2 x 2 of them, shifted blocks wrap), bf16 and fp32 modes, rel_pos False and True;
+  (b) full resolution 73 x 720 x 1440 (64,800 tokens, 400 windows), depth 1 and 2, every parameter gradient;
+  (c) BASELINE config 4: 77 input channels (field + zenith + one-hot land mask + orography), residual skip,
+      'weighted absolute temp-std squared geometric l2' through LossHandler with synthetic std files, batch 2;
+  (d) data-parallel: DDP over 2 ranks == single process on the concatenated batch (train.py:186-190).
+
+Bars (north_star): relative L2 <= 1e-2 in bf16 mode on the output and EVERY parameter gradient -- including
+`logit_scale` and the CPB `meta_mlp.*` -- and <= 1e-5 in fp32 mode (5e-5 for logit_scale).  Each test also writes its
+per-tensor error table to gpurun_out/parity_*.json so the numbers can be quoted.
+"""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import swinv2_oracle as O
+from swin_v2_weather_b200.functional import LatWeightedL2Fn
+from swin_v2_weather_b200.networks.swinv2_global import SwinTransformerV2Cr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+BF16_TOL = 1e-2
+FP32_TOL, FP32_TOL_SCALE = 1e-5, 5e-5
+
+
+def build(cfg: O.SwinConfig, sd, mode: str, **kw):
+    m = SwinTransformerV2Cr(img_size=cfg.img_size, patch_size=cfg.patch_size, depths=(cfg.depth,), num_heads=(cfg.num_heads,),
+                            in_chans=cfg.in_chans, out_chans=cfg.out_chans, embed_dim=cfg.embed_dim,
+                            img_window_ratio=cfg.window_ratio, drop_path_rate=cfg.drop_path_rate,
+                            full_pos_embed=cfg.full_pos_embed, rel_pos=cfg.rel_pos, mlp_ratio=cfg.mlp_ratio,
+                            residual=cfg.residual, compute_mode=mode, **kw)
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def inputs(cfg, batch, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, cfg.in_chans, *cfg.img_size, generator=g)
+    tar = torch.randn(batch, cfg.out_chans, *cfg.img_size, generator=g)
+    return x, tar
+
+
+def errors(pred, loss, grads, pred_ref, loss_ref, grads_ref):
+    rep = {"pred": O.rel_l2(pred, pred_ref), "loss": abs(loss - float(loss_ref)) / abs(float(loss_ref))}
+    for k, g_ref in grads_ref.items():
+        if k.endswith("meta_mlp.fc2.bias"):      # analytically zero (softmax shift invariance): compare on an absolute scale
+            scale = max(float(v.abs().max()) for kk, v in grads_ref.items() if "meta_mlp.fc2.weight" in kk)
+            rep[k] = float(grads[k].abs().max()) / scale * 1e-1    # <= 1e-2 means |g| <= 10 % of the largest fc2.weight gradient entry
+            continue
+        rep[k] = O.rel_l2(grads[k], g_ref)
+    return rep
+
+
+def oracle_autocast_distance(x, tar, sd, cfg, chw, grads_ref, relative=True):
+    """how far the reference algorithm's OWN bf16 autocast run is from its fp32 run on these inputs (CPU autocast:
+    linear / matmul in bf16, softmax / layer_norm / reductions in fp32) -- the noise floor of any bf16 implementation."""
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        _, _, g16 = O.loss_and_grads(x, tar, sd, cfg, chw, relative=relative)
+    return {k: O.rel_l2(g16[k].float(), grads_ref[k]) for k in grads_ref if not k.endswith("meta_mlp.fc2.bias")}
+
+
+def dump(name, rep, extra=None):
+    os.makedirs(OUT, exist_ok=True)
+    worst = sorted(((v, k) for k, v in rep.items()), reverse=True)[:8]
+    with open(os.path.join(OUT, f"parity_{name}.json"), "w") as f:
+        json.dump({"worst": worst, "all": rep, **(extra or {})}, f, indent=1)
+    return worst
+
+
+def assert_within(rep, tol, tol_scale=None, name=""):
+    bad = [(k, v) for k, v in rep.items()
+           if not v < ((tol_scale if (tol_scale and ("logit_scale" in k)) else tol))]
+    assert not bad, (name, bad)
+
+
+def run_ours(model, x, tar, chw, relative):
+    qw = O.quadrature_row_weights(*x.shape[-2:]).cuda()
+    model.zero_grad(set_to_none=True)
+    pred = model(x.cuda())
+    loss = LatWeightedL2Fn.apply(pred, tar.cuda(), qw, chw.cuda(), relative, True)
+    loss.backward()
+    torch.cuda.synchronize()
+    return pred.detach().cpu(), float(loss), {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+
+
+# ---- (a) headline width / heads / depth on the small image ------------------------------------------------------------------
+@pytest.mark.parametrize("rel_pos", [False, True])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_headline_model_depth12_vs_oracle(mode, rel_pos):
+    cfg = O.SwinConfig(img_size=(72, 144), depth=12, num_heads=8, in_chans=73, out_chans=73, embed_dim=768, window_ratio=8,
+                       rel_pos=rel_pos)
+    sd = O.init_state_dict(cfg, seed=11)
+    x, tar = inputs(cfg, 2)
+    chw = torch.ones(73) / 73
+    ref = O.loss_and_grads(x, tar, sd, cfg, chw, relative=True)
+    rep = errors(*run_ours(build(cfg, sd, mode), x, tar, chw, True), *ref)
+    extra = None
+    if mode == "bf16":
+        floor = oracle_autocast_distance(x, tar, sd, cfg, chw, ref[2])
+        extra = {"oracle_bf16_autocast_vs_fp32": floor, "oracle_bf16_autocast_worst": sorted(((v, k) for k, v in floor.items()), reverse=True)[:8]}
+    worst = dump(f"depth12_{mode}_{'cpb' if rel_pos else 'nopos'}", rep, extra)
+    print(mode, rel_pos, worst[:4])
+    if mode == "fp32":
+        assert_within(rep, FP32_TOL, FP32_TOL_SCALE, "depth12 fp32")
+    else:
+        assert_within(rep, BF16_TOL, None, "depth12 bf16")
+
+
+# ---- (b) full resolution ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("depth,mode", [(1, "bf16"), (2, "bf16"), (1, "fp32")])
+def test_full_resolution_vs_oracle(depth, mode):
+    """73 x 720 x 1440, C = 768, 8 heads, 400 windows of 162 tokens: output, loss and every gradient (incl. the 199 MB
+    pos_embed gradient) against the CPU oracle.  networks/swinv2_global.py:794-803, utils/losses.py:208-232."""
+    cfg = O.SwinConfig(depth=depth)            # defaults = swin_73var_geo_depth12 geometry
+    sd = O.init_state_dict(cfg, seed=2)
+    x, tar = inputs(cfg, 1, seed=5)
+    chw = torch.ones(73) / 73
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = O.loss_and_grads(x, tar, sd, cfg, chw, relative=True)
+    rep = errors(*run_ours(build(cfg, sd, mode), x, tar, chw, True), *ref)
+    worst = dump(f"fullres_d{depth}_{mode}", rep)
+    print(depth, mode, worst[:4])
+    if mode == "fp32":
+        assert_within(rep, FP32_TOL, FP32_TOL_SCALE, "full-res fp32")
+    else:
+        assert_within(rep, BF16_TOL, None, "full-res bf16")
+
+
+# ---- (c) BASELINE config 4 ----------------------------------------------------------------------------------------------------
+def test_config4_conditioning_weighted_tempstd_loss(tmp_path):
+    """Cin = 77 (73 + zenith + 2 land-mask classes + orography) as channel groups, residual skip, LossHandler with the
+    'auto' channel table x temp-std ratio (utils/losses.py:56-99), batch 2, full resolution, one block -- against the oracle
+    on the concatenated input and the restated LossHandler."""
+    from swin_v2_weather_b200.utils.losses import LossHandler
+    from swin_v2_weather_b200.utils.preprocess_utils import PreProcessor
+    H, W, B = 720, 1440, 2
+    cfg = O.SwinConfig(depth=1, in_chans=77, out_chans=73, residual=True)
+    sd = O.init_state_dict(cfg, seed=4)
+    g = torch.Generator().manual_seed(9)
+    field = torch.randn(B, 73, H, W, generator=g)
+    tar = torch.randn(B, 73, H, W, generator=g)
+    zen = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    lsm = (torch.rand(H, W, generator=g) > 0.7).long()
+    oro = torch.randn(H, W, generator=g)
+    rng = np.random.default_rng(7)
+    gstd = np.ones((1, 73, 1, 1), dtype=np.float32)
+    tstd = rng.uniform(0.2, 1.0, size=(1, 73, 1, 1)).astype(np.float32)
+    np.save(tmp_path / "gs.npy", gstd)
+    np.save(tmp_path / "ts.npy", tstd)
+    loss_name = 'weighted absolute temp-std squared geometric l2'
+    lp = SimpleNamespace(n_future=0, img_shape_x=H, img_shape_y=W, loss=loss_name, channel_weights='auto', n_out_channels=73,
+                         channel_names=list(O.CHANNEL_NAMES_73), out_channels=list(range(73)), dt=1, model_grid_type='equiangular',
+                         global_stds_path=str(tmp_path / "gs.npy"), time_diff_stds_path=str(tmp_path / "ts.npy"))
+    lossf = LossHandler(lp).cuda().train()
+    chw = O.loss_handler_channel_weights(loss_name, 'auto', lp.channel_names, 73, lp.out_channels, 1, gstd, tstd)
+    assert torch.equal(lossf.channel_weights.reshape(-1).cpu(), chw)
+    pp = SimpleNamespace(img_size=(H, W), add_landmask=True, add_orography=True, add_zenith=True, landmask=lsm, orography=oro)
+    pre = PreProcessor(pp, "cuda").cuda()
+    groups, tar_d, _ = pre((field, tar, zen, zen))
+    assert isinstance(groups, tuple) and [t.shape[1] for t in groups] == [73, 1, 3]
+    # oracle: concatenated input, restated LossHandler
+    static = torch.cat([torch.nn.functional.one_hot(lsm).permute(2, 0, 1).float()[None], ((oro - oro.mean()) / (oro.std() + 1e-6))[None, None]], 1)
+    x_cat = torch.cat([field, zen, static.expand(B, -1, -1, -1)], dim=1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    pred_ref = O.model_forward(x_cat, leaves, cfg)
+    loss_ref = O.loss_handler(pred_ref, tar, loss_name, chw, n_future=0, training=True)
+    grads_ref = dict(zip(leaves.keys(), torch.autograd.grad(loss_ref, list(leaves.values()))))
+    model = build(cfg, sd, "bf16")
+    pred = model(groups)
+    loss = lossf(pred, tar_d, None)
+    loss.backward()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    rep = errors(pred.detach().cpu(), float(loss), grads, pred_ref.detach(), loss_ref.detach(), grads_ref)
+    worst = dump("config4_bf16", rep)
+    print(worst[:4])
+    assert_within(rep, BF16_TOL, None, "config 4")
+
+
+# ---- (d) data-parallel gradient equivalence ---------------------------------------------------------------------------------------
+def _ddp_worker(rank, world, port, backend, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank if backend == "nccl" else 0))
+    import torch.distributed as dist
+    from swin_v2_weather_b200 import distributed as D
+    dev = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    cfg = O.SwinConfig(img_size=(72, 144), depth=3, num_heads=8, in_chans=73, out_chans=73, embed_dim=768, window_ratio=8)
+    sd = O.init_state_dict(cfg, seed=21)
+    x, tar = inputs(cfg, 2 * world, seed=77)
+    chw = torch.ones(73) / 73
+    qw = O.quadrature_row_weights(72, 144).cuda()
+    model = build(cfg, sd, "bf16").train()
+    ddp = D.wrap_ddp(model, dev, bucket_cap_mb=4)
+    idx = list(D.shard_indices(2 * world, rank, world))
+    pred = ddp(x[idx].cuda())
+    loss = LatWeightedL2Fn.apply(pred, tar[idx].cuda(), qw, chw.cuda(), True, True)
+    loss.backward()
+    torch.cuda.synchronize()
+    torch.save({k: p.grad.detach().cpu() for k, p in model.named_parameters()}, os.path.join(tmpdir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("backend", ["gloo", "nccl"])
+def test_ddp_gradients_equal_single_process(backend, tmp_path):
+    """wrap_ddp over 2 ranks (NCCL on two GPUs when the box has them; gloo with both ranks on cuda:0 otherwise covers the
+    bucket-view / autograd-hook plumbing on the real model) == one process on the whole batch, gradients / world."""
+    import torch.multiprocessing as mp
+    world = 2
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("NCCL needs one GPU per rank")
+    port = 29650 + (os.getpid() % 200) + (0 if backend == "gloo" else 1)
+    mp.spawn(_ddp_worker, args=(world, port, backend, str(tmp_path)), nprocs=world, join=True)
+    cfg = O.SwinConfig(img_size=(72, 144), depth=3, num_heads=8, in_chans=73, out_chans=73, embed_dim=768, window_ratio=8)
+    sd = O.init_state_dict(cfg, seed=21)
+    x, tar = inputs(cfg, 2 * world, seed=77)
+    chw = torch.ones(73) / 73
+    _, _, g_single = run_ours(build(cfg, sd, "bf16").train(), x, tar, chw, True)
+    g0 = torch.load(os.path.join(tmp_path, "g0.pt"))
+    g1 = torch.load(os.path.join(tmp_path, "g1.pt"))
+    rep = {}
+    for k in g_single:
+        assert torch.equal(g0[k], g1[k]), f"ranks disagree on {k} after the all-reduce"
+        rep[k] = O.rel_l2(g0[k], g_single[k] / world)
+    worst = dump(f"ddp_{backend}", rep)
+    print(worst[:3])
+    # same kernels on the same samples: only the fp32 summation order (atomics, all-reduce) differs
+    assert max(rep.values()) < 2e-3, worst[:5]

@@ -1,0 +1,113 @@
+"""GPU parity of the SURVEY 8(f) rank 3-4 additions against the oracle restatements (which are pinned to the live reference
+in tests/test_oracle_vs_reference.py): L1 and pole-masked losses through LossHandler, the anomaly-correlation metric, the
+GELU tail, and the input z-score folded into the PatchEmbed im2col / residual skip."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import swinv2_oracle as O
+from swin_v2_weather_b200 import ops
+from swin_v2_weather_b200._lib import BACKEND_TCGEN05, EPI_BIAS_GELU
+from swin_v2_weather_b200.networks.swinv2_global import SwinTransformerV2Cr
+
+pytestmark = pytest.mark.gpu
+
+
+def _handler(loss, C, H, W, n_future=0):
+    from swin_v2_weather_b200.utils.losses import LossHandler
+    p = SimpleNamespace(n_future=n_future, img_shape_x=H, img_shape_y=W, loss=loss, channel_weights='auto', n_out_channels=C,
+                        channel_names=list(O.CHANNEL_NAMES_73)[:C], out_channels=list(range(C)), dt=1, model_grid_type='equiangular')
+    return LossHandler(p).cuda().train(), O.loss_handler_channel_weights(loss, 'auto', p.channel_names, C)
+
+
+@pytest.mark.parametrize("loss", ["weighted geometric l1", "absolute geometric l1", "l1", "weighted pole-masked geometric l1",
+                                  "pole-masked absolute squared geometric l2", "weighted pole-masked geometric l2", "l2"])
+def test_loss_variants_vs_oracle(loss):
+    """utils/losses.py:101-124 (+ utils/grids.py:96-99 for 'pole-masked'): value and dL/dprd."""
+    C, H, W = 11, 36, 72
+    lossf, chw = _handler(loss, C, H, W)
+    g = torch.Generator().manual_seed(4)
+    prd = torch.randn(3, C, H, W, generator=g)
+    tar = torch.randn(3, C, H, W, generator=g)
+    p_ref = prd.clone().requires_grad_(True)
+    l_ref = O.loss_handler(p_ref, tar, loss, chw)
+    g_ref, = torch.autograd.grad(l_ref, p_ref)
+    p_dev = prd.cuda().requires_grad_(True)
+    l = lossf(p_dev, tar.cuda(), None)
+    l.backward()
+    assert abs(float(l) - float(l_ref)) <= 2e-6 * abs(float(l_ref))
+    assert O.rel_l2(p_dev.grad, g_ref) < 1e-5
+    if "pole-masked" in loss:
+        assert float(p_dev.grad[:, :, 0].abs().max()) == 0.0 and float(p_dev.grad[:, :, -1].abs().max()) == 0.0
+
+
+def test_loss_rejects_mismatched_shapes():
+    lossf, _ = _handler("geometric l2", 5, 36, 72)
+    with pytest.raises((ValueError, RuntimeError)):
+        lossf(torch.zeros(1, 5, 40, 72, device="cuda"), torch.zeros(1, 5, 40, 72, device="cuda"), None)
+    with pytest.raises((ValueError, RuntimeError)):
+        lossf(torch.zeros(1, 5, 36, 72, device="cuda"), torch.zeros(1, 4, 36, 72, device="cuda"), None)
+
+
+def test_weighted_acc_vs_oracle():
+    from swin_v2_weather_b200.utils.weighted_acc_rmse import weighted_acc_torch, weighted_acc_torch_channels
+    g = torch.Generator().manual_seed(8)
+    pred = torch.randn(3, 7, 37, 72, generator=g)
+    tar = 0.6 * pred + 0.8 * torch.randn(3, 7, 37, 72, generator=g)
+    want = O.weighted_acc_channels(pred, tar)
+    got = weighted_acc_torch_channels(pred.cuda(), tar.cuda()).cpu()
+    assert torch.allclose(got, want, rtol=2e-5, atol=1e-6)
+    assert torch.allclose(weighted_acc_torch(pred.cuda(), tar.cuda()).cpu(), want.mean(0), rtol=2e-5, atol=1e-6)
+    # full-size field: one pass, same answer
+    pred = torch.randn(1, 3, 720, 1440, generator=g)
+    tar = pred + torch.randn(1, 3, 720, 1440, generator=g)
+    assert torch.allclose(weighted_acc_torch_channels(pred.cuda(), tar.cuda()).cpu(), O.weighted_acc_channels(pred, tar), rtol=5e-5)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_input_zscore_folded_into_patch_embed(mode):
+    """Raw field + (mean, std) through the model == oracle on the z-scored field (data_loader_era5_dali.py:77-90), with the
+    residual skip reading the same normalised values and the appended conditioning channels passing through unchanged."""
+    cfg = O.SwinConfig(img_size=(72, 144), depth=2, num_heads=2, in_chans=8, out_chans=5, embed_dim=192, window_ratio=8,
+                       residual=True)
+    sd = O.init_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(12)
+    mean = torch.randn(5, generator=g) * 50 + 200
+    std = torch.rand(5, generator=g) * 20 + 1
+    raw = torch.randn(2, 5, 72, 144, generator=g) * std.view(1, 5, 1, 1) + mean.view(1, 5, 1, 1)
+    cond = torch.rand(2, 3, 72, 144, generator=g)
+    tar = torch.randn(2, 5, 72, 144, generator=g)
+    chw = torch.ones(5) / 5
+    x_ref = torch.cat([O.zscore(raw, mean, std), cond], dim=1)
+    pred_ref, loss_ref, grads_ref = O.loss_and_grads(x_ref, tar, sd, cfg, chw, relative=False)
+    m = SwinTransformerV2Cr(img_size=cfg.img_size, patch_size=4, depths=(2,), num_heads=(2,), in_chans=8, out_chans=5, embed_dim=192,
+                            img_window_ratio=8, full_pos_embed=True, rel_pos=False, residual=True, compute_mode=mode)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    from swin_v2_weather_b200.functional import LatWeightedL2Fn
+    qw = O.quadrature_row_weights(72, 144).cuda()
+    for inp in ((raw.cuda(), cond.cuda()), torch.cat([raw, cond], 1).cuda()):
+        m.zero_grad(set_to_none=True)
+        pred = m(inp, input_stats=(mean, std))
+        loss = LatWeightedL2Fn.apply(pred, tar.cuda(), qw, chw.cuda(), False, True)
+        loss.backward()
+        tol = 1e-5 if mode == "fp32" else 1e-2
+        assert O.rel_l2(pred, pred_ref) < tol
+        for k, p in m.named_parameters():
+            lim = (5e-5 if mode == "fp32" else 5e-2) if "logit_scale" in k else tol
+            assert O.rel_l2(p.grad, grads_ref[k]) < lim, k
+
+
+def test_gelu_epilogue_tails():
+    """pre-activations far outside the polynomial's clamp range must not grow a linear error."""
+    T, K, N = 256, 64, 256
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(T, K, generator=g).cuda().bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.01).cuda().bfloat16()
+    bias = torch.linspace(-60, 60, N).cuda()
+    gel, h = ops.gemm(ops.MODE_BF16, a, 0, w, 0, EPI_BIAS_GELU, bias=bias, backend=BACKEND_TCGEN05)
+    want = torch.nn.functional.gelu(h.float())
+    err = (gel.float() - want).abs()
+    assert float(err[h.float() < -4].max()) < 2e-4          # exact value tends to 0-; ours is bounded by 4 * Phi(-4)
+    assert float((err / want.abs().clamp_min(1.0)).max()) < 1e-2
