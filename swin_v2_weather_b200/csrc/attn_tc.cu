@@ -14,13 +14,9 @@
 // forward:   S = Q^ K^T (tcgen05, TMEM) -> thread-per-row softmax(scale*S + bias + mask) -> P (bf16, smem)
 //            -> O = P V (tcgen05, accumulator aliases S) -> O / rowsum -> scatter to (T, C); row LSE saved.
 #include <stdlib.h>
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attn_tc.cuh"
 
 namespace swinb200 {
-using namespace ptx;
-
-constexpr int kMaxLP = 176;  // padded keys per window (multiple of 16); 9x18 = 162 -> 176
 
 // optional per-phase cycle stamps (bring-up aid): when non-null, CTA b writes clock64() deltas to g_phase[b*16 + i]
 __device__ long long* g_phase_buf = nullptr;
@@ -28,44 +24,6 @@ __device__ long long* g_phase_buf = nullptr;
   do {                                                                               \
     if (g_phase_buf != nullptr && threadIdx.x == 0 && blockIdx.x < 4096) g_phase_buf[blockIdx.x * 16 + (i)] = clock64(); \
   } while (0)
-
-__host__ __device__ constexpr uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-struct AttnGeom {
-  int B, H, W, C, heads, Wh, Ww, s0, s1;
-  int L, LP, nW, nWw;
-};
-
-__device__ __forceinline__ int win_token(const AttnGeom& g, int b, int w, int n, int& rolled_row) {
-  const int wh = w / g.nWw, ww = w - wh * g.nWw;
-  const int a = n / g.Ww, c = n - a * g.Ww;
-  rolled_row = wh * g.Wh + a;
-  int i = rolled_row + g.s0;
-  if (i >= g.H) i -= g.H;
-  int j = ww * g.Ww + c + g.s1;
-  if (j >= g.W) j -= g.W;
-  return (b * g.H + i) * g.W + j;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float as_f(uint32_t u) { return __uint_as_float(u); }
-__device__ __forceinline__ uint4 pack8(const float (&v)[16], int o) {
-  uint4 r;
-  r.x = pack_bf16x2(v[o + 0], v[o + 1]); r.y = pack_bf16x2(v[o + 2], v[o + 3]);
-  r.z = pack_bf16x2(v[o + 4], v[o + 5]); r.w = pack_bf16x2(v[o + 6], v[o + 7]);
-  return r;
-}
 
 // Row tiles leave the kernel through shared memory: each thread parks its [1 x D] bf16 row (pitch kRowPitch keeps the
 // 16-byte stores conflict-free), then the CTA writes token rows with consecutive threads on consecutive 16-byte pieces,
@@ -374,25 +332,6 @@ struct Fwd2Smem {
   static constexpr int kBytes = kOffBar + 64;
 };
 
-__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint4& v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint4& a, const uint4& b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y),
-               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 template <int D>
 __global__ void __launch_bounds__(128, 2)
 attn_tc_fwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ scale_p, const float* __restrict__ bias,
@@ -624,7 +563,7 @@ int attn_set_phase_buffer(long long* buf) {
   return SWINB200_OK;
 }
 
-static int make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
+int attn_make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
   g.B = B; g.H = H; g.W = W; g.C = C; g.heads = heads; g.Wh = Wh; g.Ww = Ww; g.s0 = s0; g.s1 = s1;
   g.L = Wh * Ww;
   g.LP = (g.L + 15) / 16 * 16;
@@ -644,7 +583,7 @@ static int make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh,
 int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, void* o, float* lse, int B, int H, int W, int C,
                      int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
   AttnGeom g;
-  if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
+  if (int e = attn_make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_FWD");
@@ -1114,21 +1053,6 @@ attn_tc_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
 // rows of the un-swizzled layout).  The same bytes serve as K-major operands (rows = m/n, k along the row: 8-row groups
 // 512 B apart, k advances 32 B inside the row, 32-k chunks a chunk stride apart) and as MN-major operands (rows = k:
 // 8-k groups 512 B apart, 32-wide n chunks a chunk stride apart, k advances 16 rows = 1024 B).
-constexpr int kCS64 = kMaxLP * 64;          // chunk stride: 11,264 B = 22 x 512
-__host__ __device__ constexpr uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61) /* SWIZZLE_64B */;
-}
-__device__ __forceinline__ uint64_t opnd_kmajor(uint32_t base, int k, int row0) {   // k-th 16-wide k step, rows from row0
-  return umma_desc_sw64(base + (uint32_t)((k >> 1) * kCS64 + (k & 1) * 32 + row0 * 64), 16, 512);
-}
-__device__ __forceinline__ uint64_t opnd_mnmajor(uint32_t base, int k) {             // k-th group of 16 rows (= k dimension)
-  return umma_desc_sw64(base + (uint32_t)(k * 1024), kCS64, 512);
-}
-// byte offset of the 16-byte piece `piece` (0..11) of row `row` inside an operand tile
-__device__ __forceinline__ uint32_t opnd_off(int row, int piece) {
-  return (uint32_t)((piece >> 2) * kCS64 + row * 64 + (((piece & 3) ^ ((row >> 1) & 3)) << 4));
-}
 template <int D>
 struct Bwd2Smem {
   static constexpr int kChunks = D / 8;
@@ -1148,13 +1072,6 @@ struct Bwd2Smem {
   static constexpr int kBytes = kOffDsc + 128;
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
-
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 
 template <int D>
 __global__ void __launch_bounds__(256, 1)
@@ -1666,7 +1583,7 @@ EncodeTiledFn get_encode_tiled();
 
 // (B, H, W, channels) bf16 activation seen as [32 | channels/32 | W | H | B]; one box = a 32-channel (64-byte) column of a
 // window, written 64B-swizzled
-static int make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int channels, int Wh, int Ww) {
+int attn_make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int channels, int Wh, int Ww) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -1694,7 +1611,7 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
                      const void* d_o, const float* lse, void* dqkv, float* dscale, float* dbias, float* ws, int B, int H, int W,
                      int C, int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
   AttnGeom g;
-  if (int e = make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
+  if (int e = attn_make_geom(g, B, H, W, C, heads, Wh, Ww, s0, s1)) return e;
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_BWD");
@@ -1719,8 +1636,8 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
       configured2 = true;
     }
     CUtensorMap tm_qkv, tm_do;
-    if (int e = make_window_tmap(&tm_qkv, qkv, B, H, W, 3 * C, Wh, Ww)) return e;
-    if (int e = make_window_tmap(&tm_do, d_o, B, H, W, C, Wh, Ww)) return e;
+    if (int e = attn_make_window_tmap(&tm_qkv, qkv, B, H, W, 3 * C, Wh, Ww)) return e;
+    if (int e = attn_make_window_tmap(&tm_do, d_o, B, H, W, C, Wh, Ww)) return e;
     const long long n_pairs = (long long)B * H * W * heads;
     attn_rowdot_kernel<<<(unsigned)((n_pairs * 4 + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
                                                                                   ws, n_pairs, C / heads);

@@ -130,7 +130,11 @@ def test_loss_handler_parsing():
     assert h.multistep_weight.reshape(-1).tolist() == [0.5, 0.5]
     h = LossHandler(SimpleNamespace(loss='l2', **base))
     assert not h.loss_obj.absolute and not h.loss_obj.squared
+    h = LossHandler(SimpleNamespace(loss='pole-masked geometric l1', **base))
+    assert h.loss_obj.p == 1 and h.loss_obj.pole_mask == 1 and not h.loss_obj.absolute
+    qw = h.loss_obj.quadrature.quad_row_weight
+    assert float(qw[0]) == 0.0 and float(qw[-1]) == 0.0 and float(qw[1]) > 0.0
     with pytest.raises(NotImplementedError):
-        LossHandler(SimpleNamespace(loss='geometric l1', **base))
+        LossHandler(SimpleNamespace(loss='geometric h1', **base))
     with pytest.raises(ValueError):
         LossHandler(SimpleNamespace(loss='huber', **base))
