@@ -97,6 +97,5 @@ int attn_make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, i
 int attn_make_window_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int channels, int Wh, int Ww);
 int attn_tcgen05_bwd3(const void* qkv, const float* inv_norm, const float* scale, const float* bias, const void* o, const void* d_o,
                       const float* lse, void* dqkv, float* dscale, float* dbias, float* ws, const AttnGeom& g, cudaStream_t stream);
-extern __device__ long long* g_phase_buf;
 
 }  // namespace swinb200
