@@ -558,9 +558,10 @@ attn_tc_fwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
   }
 }
 
+int attn_set_phase_buffer3(long long* buf);
 int attn_set_phase_buffer(long long* buf) {
   SWB_CUDA(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
-  return SWINB200_OK;
+  return attn_set_phase_buffer3(buf);
 }
 
 int attn_make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, int Ww, int s0, int s1) {
@@ -1615,9 +1616,11 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_BWD");
-    variant = e ? atoi(e) : 2;   // 1 = one CTA per (window, head);  2 = persistent CTAs fed by TMA boxes (needs ws)
+    variant = e ? atoi(e) : 3;   // 1 = one CTA per (window, head);  2 = persistent two-sweep kernel;  3 = single-pass warp-specialised
   }
   const bool aligned = ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)d_o % 16 == 0);
+  if (variant == 3 && ws != nullptr && aligned)
+    return attn_tcgen05_bwd3(qkv, inv_norm, scale, bias, o, d_o, lse, dqkv, dscale, dbias, ws, g, stream);
   if (variant == 1 || ws == nullptr || !aligned) {
     using SM = BwdSmem<96>;
     static bool configured = false;
