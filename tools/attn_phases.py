@@ -28,7 +28,7 @@ for shift in ((0, 0), (4, 9)):
             d = (st[:, 1:n] - st[:, 0:n - 1])
             print(name, shift, "mean cycles per phase:", [int(v) for v in d.mean(0).tolist()], "total", int((st[:, n - 1] - st[:, 0]).mean()))
         else:   # persistent kernel: per-CTA accumulated cycles per phase over all its items
-            st = buf.view(4096, 16)[:148, :12].double()
+            st = buf.view(4096, 16)[:148, :16].double()
             items = 3200 / 148
             print(name, shift, "mean cycles per phase per item:", [int(v / items) for v in st.mean(0).tolist()], "total/item", int(st.sum(1).mean() / items))
         # timing
