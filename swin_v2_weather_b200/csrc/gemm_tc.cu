@@ -60,7 +60,8 @@ struct GemmCfg {
   static constexpr int kOffStaging = kStages * kStage;
   static constexpr int kOffBars = kOffStaging + kEpiGroups * 4 * kStagingBufs * kStagingBytes;
   static constexpr int kOffBias = kOffBars + 256;
-  static constexpr int kSmem = kOffBias + kBiasBytes;
+  static constexpr int kOffSsq = kOffBias + kBiasBytes;               // BIAS_QKNORM: [2 tile parities][BN/32 pieces][128 rows] partial sums of squares
+  static constexpr int kSmem = kOffSsq + ((BN == 192) ? 2 * (BN / 32) * GBM * 4 : 0);
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
@@ -417,13 +418,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned char* stg_base = smem + Cfg::kOffStaging + ew * kStagingBufs * kStagingBytes;
     uint32_t stg_sel = 0;                  // staging buffer of the next piece
     // Each warp stages and stores its own 32 rows: no cross-warp barrier sits between tcgen05.ld and the TMA store.
-    constexpr bool kBiasEpi = (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU);
+    constexpr bool kBiasEpi = (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU || EPI == SWINB200_EPI_BIAS_QKNORM);
     constexpr int kChunksPerGroup = (kNumChunks + kEpiGroups - 1) / kEpiGroups;
     constexpr int kBiasSlots = kChunksPerGroup * kChunkCols;
     static_assert(!kBiasEpi || kBiasSlots <= 64, "bias slices must fit");
     float* sbias_grp = reinterpret_cast<float*>(smem + Cfg::kOffBias) + grp * 64;   // + 256 floats for odd tiles
     const bool has_bias = kBiasEpi && p.bias != nullptr;
     const int mrow0 = quarter * 32;        // first tile row of this warp
+    int qk_tiles = 0;                      // BIAS_QKNORM: tiles that exchanged norms so far
     int local = 0;
     for (int tile = cta_first; tile >= 0; tile = next_tile(tile, local, false), ++local) {
       const int rest = tile / p.split_k;
@@ -454,59 +456,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // epilogue operand (h for DGELU, the fp32 residual gradient for ADD_F32): 64 bytes per row per chunk, fetched one
       // chunk ahead into registers so its latency hides behind the previous chunk's arithmetic
       if (EPI == SWINB200_EPI_BIAS_QKNORM) {
-        // one head (96 columns = 3 chunks) per epilogue group (groups 0 and 1; the MMA bounds this GEMM):
-        // bias, L2 norm over the head, scale, stage, store
-        const int nh0 = n0 + grp * 96;                      // first column of this group's head
-        if (grp >= 2 || nh0 >= p.N) {                        // idle groups / odd C/96: the last tile holds one head
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
-          continue;
-        }
-        const bool normalise = nh0 < (p.N / 3) * 2;          // q and k thirds only
-        float v[96];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          uint32_t rr[32];
-          tmem_ld_32x32(t_row + grp * 96 + q * 32, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[q * 32 + i] = __uint_as_float(rr[i]);
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 24; ++g) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nh0 + g * 4));
-            v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-          }
-        }
+        // BN = 192 = two heads of 96 columns = six 32-column pieces.  Piece p belongs to group p % 4 (groups 0 and 1 own
+        // two pieces, groups 2 and 3 one), so at most 64 accumulator columns are live per thread (the one-head-per-group
+        // version held 96 and spilled under the 96-register cap).  The squared norm of a head is the sum of three pieces
+        // held by three different groups: partials go through shared memory, one named barrier per tile.
+        constexpr int kPiecesPerTile = BN / 32;                      // 6
+        const bool normalise = n0 < (p.N / 3) * 2;                    // q and k thirds only (a tile is two whole heads: it never straddles)
+        // [piece][row], double-buffered over the tiles that exchange norms: a warp can be at most one barrier ahead
+        float* ssq = reinterpret_cast<float*>(smem + Cfg::kOffSsq) + (qk_tiles & 1) * kPiecesPerTile * GBM;
+        if (normalise) ++qk_tiles;
+        // pass 1: squared-norm partials of this group's pieces (accumulator + bias, nothing kept in registers)
         if (normalise) {
-          float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < 96; ++i) ss = fmaf(v[i], v[i], ss);
-          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+          for (int j = 0; j < 2; ++j) {
+            const int pc = grp + j * kEpiGroups;
+            if (pc < kPiecesPerTile && n0 + pc * 32 < p.N) {             // uniform across the group
+              uint32_t rr[32];
+              tmem_ld_32x32(t_row + pc * 32, rr);
+              tmem_ld_wait();
+              float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < 96; ++i) v[i] *= inv;
-          if (row_ok) p.inv_norm[(size_t)m * ((p.N / 3) * 2 / 96) + nh0 / 96] = inv;
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
-          stg_sel ^= 1;
-          if (lane == 0) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[q * 32 + c * 8 + 0], v[q * 32 + c * 8 + 1]); pk.y = pack_bf16x2(v[q * 32 + c * 8 + 2], v[q * 32 + c * 8 + 3]);
-            pk.z = pack_bf16x2(v[q * 32 + c * 8 + 4], v[q * 32 + c * 8 + 5]); pk.w = pack_bf16x2(v[q * 32 + c * 8 + 6], v[q * 32 + c * 8 + 7]);
-            *reinterpret_cast<uint4*>(staging_chunk(stg0, lane, c)) = pk;
+              for (int g4 = 0; g4 < 8; ++g4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias) b4 = *reinterpret_cast<const float4*>(sbias + j * 32 + g4 * 4);
+                const float a0 = __uint_as_float(rr[g4 * 4 + 0]) + b4.x, a1 = __uint_as_float(rr[g4 * 4 + 1]) + b4.y;
+                const float a2 = __uint_as_float(rr[g4 * 4 + 2]) + b4.z, a3 = __uint_as_float(rr[g4 * 4 + 3]) + b4.w;
+                ss = fmaf(a0, a0, ss); ss = fmaf(a1, a1, ss); ss = fmaf(a2, a2, ss); ss = fmaf(a3, a3, ss);
+              }
+              ssq[pc * GBM + r] = ss;
+            }
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmD, stg0, nh0 + q * 32, m0 + mrow0);
-            bulk_commit();
+          asm volatile("bar.sync 5, %0;" ::"r"(kEpiGroups * 128) : "memory");   // all epilogue warps (uniform per tile)
+        }
+        // pass 2: accumulator again (tensor memory is cheap to re-read, 64 live fp32 values are not under a 96-register
+        // cap) + bias, scaled by the head's reciprocal norm, staged and stored
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int pc = grp + j * kEpiGroups;
+          const int nb = n0 + pc * 32;
+          if (pc < kPiecesPerTile && nb < p.N) {
+            uint32_t rr[32];
+            tmem_ld_32x32(t_row + pc * 32, rr);
+            float inv = 1.0f;
+            if (normalise) {
+              const int hp = (pc / 3) * 3;                              // first piece of this piece's head
+              const float tot = ssq[hp * GBM + r] + ssq[(hp + 1) * GBM + r] + ssq[(hp + 2) * GBM + r];
+              inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+              if (pc == hp && row_ok) p.inv_norm[(size_t)m * ((p.N / 3) * 2 / 96) + nb / 96] = inv;
+            }
+            unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
+            stg_sel ^= 1;
+            if (lane == 0) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+            __syncwarp();
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float o8[8];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias) b4 = *reinterpret_cast<const float4*>(sbias + j * 32 + c * 8 + h2 * 4);
+                o8[h2 * 4 + 0] = (__uint_as_float(rr[c * 8 + h2 * 4 + 0]) + b4.x) * inv;
+                o8[h2 * 4 + 1] = (__uint_as_float(rr[c * 8 + h2 * 4 + 1]) + b4.y) * inv;
+                o8[h2 * 4 + 2] = (__uint_as_float(rr[c * 8 + h2 * 4 + 2]) + b4.z) * inv;
+                o8[h2 * 4 + 3] = (__uint_as_float(rr[c * 8 + h2 * 4 + 3]) + b4.w) * inv;
+              }
+              uint4 pk;
+              pk.x = pack_bf16x2(o8[0], o8[1]); pk.y = pack_bf16x2(o8[2], o8[3]);
+              pk.z = pack_bf16x2(o8[4], o8[5]); pk.w = pack_bf16x2(o8[6], o8[7]);
+              *reinterpret_cast<uint4*>(staging_chunk(stg0, lane, c)) = pk;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmD, stg0, nb, m0 + mrow0);
+              bulk_commit();
+            }
           }
         }
         tc_fence_before();

@@ -20,6 +20,7 @@ dxo = torch.randn(T, C, device="cuda")
 m = ops.MODE_BF16
 cases = {
  "qkv fwd   (BIAS)     ": (2*T*3*C*C, lambda: ops.gemm(m, x, 0, w_qkv, 0, EPI_BIAS, bias=b3)),
+ "qkv fwd   (BIAS_QKNORM)": (2*T*3*C*C, lambda: ops.qkv_projection(m, x, w_qkv, b3, C, 8)),
  "fc1 fwd   (BIAS_GELU)": (2*T*HID*C, lambda: ops.gemm(m, x, 0, w_fc1, 0, EPI_BIAS_GELU, bias=bh)),
  "fc2 fwd   (BIAS)     ": (2*T*HID*C, lambda: ops.gemm(m, g, 0, w_fc2, 0, EPI_BIAS, bias=bc)),
  "fc2 dgrad (DGELU)    ": (2*T*HID*C, lambda: ops.gemm(m, dz, 0, w_fc2, 1, EPI_DGELU, aux=h)),
