@@ -25,32 +25,6 @@ __device__ long long* g_phase_buf = nullptr;
     if (g_phase_buf != nullptr && threadIdx.x == 0 && blockIdx.x < 4096) g_phase_buf[blockIdx.x * 16 + (i)] = clock64(); \
   } while (0)
 
-// Row tiles leave the kernel through shared memory: each thread parks its [1 x D] bf16 row (pitch kRowPitch keeps the
-// 16-byte stores conflict-free), then the CTA writes token rows with consecutive threads on consecutive 16-byte pieces,
-// so every global store instruction covers whole 192-byte rows instead of 32 scattered 16-byte fragments.
-constexpr int kRowPitch = 208;
-template <int D>
-__device__ __forceinline__ void park_row(unsigned char* stage, int row, const float (&v)[D]) {
-#pragma unroll
-  for (int c = 0; c < D / 8; ++c) {
-    uint4 pk;
-    pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-    pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-    *reinterpret_cast<uint4*>(stage + row * kRowPitch + c * 16) = pk;
-  }
-}
-// rows [0, nrows) of `stage` -> dst[tok[slot0 + row] * ld + col0 ...]; executed by `nthr` threads with index `t`
-template <int D>
-__device__ __forceinline__ void scatter_rows(const unsigned char* stage, int nrows, const int* tok, int slot0,
-                                             __nv_bfloat16* dst, int ld, int col0, int t, int nthr) {
-  constexpr int kPieces = D / 8;
-  for (int i = t; i < nrows * kPieces; i += nthr) {
-    const int row = i / kPieces, c = i - row * kPieces;
-    const uint4 v = *reinterpret_cast<const uint4*>(stage + row * kRowPitch + c * 16);
-    *reinterpret_cast<uint4*>(dst + (size_t)tok[slot0 + row] * ld + col0 + c * 8) = v;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
@@ -588,8 +562,10 @@ int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, voi
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_FWD");
-    variant = e ? atoi(e) : 2;
+    variant = e ? atoi(e) : 3;   // 1 = first SS-mode kernel; 2 = two CTAs per SM, cp.async gather; 3 = persistent, TMA boxes, double-buffered
   }
+  if (variant == 3 && ((uintptr_t)qkv % 16 == 0) && g.L * kRowPitch <= (96 / 32) * kCS64)
+    return attn_tcgen05_fwd3(qkv, scale, bias, o, lse, g, stream);
   if (variant == 1) {
     using SM = FwdSmem<96>;
     static bool configured = false;

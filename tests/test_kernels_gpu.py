@@ -244,6 +244,7 @@ def test_window_attention_simt(dtype, cfg):
     dict(B=1, H=12, W=24, C=192, heads=2, window=(6, 12), shift=(3, 6), bias=True),
     dict(B=1, H=27, W=36, C=96, heads=1, window=(9, 18), shift=(4, 0), bias=False),
     dict(B=1, H=18, W=54, C=96, heads=1, window=(9, 18), shift=(0, 9), bias=False),
+    dict(B=1, H=18, W=36, C=192, heads=2, window=(9, 18), shift=(0, 0), bias=False, scale=[8.0, 95.0]),   # exact-max softmax path
 ])
 def test_window_attention_tcgen05(cfg):
     B, H, W, C, heads = cfg["B"], cfg["H"], cfg["W"], cfg["C"], cfg["heads"]
@@ -251,7 +252,7 @@ def test_window_attention_tcgen05(cfg):
     L = window[0] * window[1]
     T = B * H * W
     raw = gen(T, 3 * C, seed=20).to(torch.bfloat16)
-    scale = torch.tensor([10.0, 13.5][:heads], device=DEV)
+    scale = torch.tensor(cfg.get("scale", [10.0, 13.5])[:heads], device=DEV)
     bias = (0.5 * gen(heads, L, L, seed=21)) if cfg["bias"] else None
     o_ref, lse_ref = oracle_attention(raw.float(), scale, bias, B, H, W, C, heads, window, shift)
     qkv = raw.clone()
