@@ -132,7 +132,9 @@ int swinb200_colsum(const void* x, int act_dtype, float* out, int rows, int cols
  *   bias: nullable (heads, L, L) fp32 (continuous position bias table, :274-287).  The shift mask
  *   ({0,-100}, :403-424) is generated in-kernel from (H, Wh, s0); swinb200_shift_mask materialises the
  *   same predicate as the reference's (nW, L, L) buffer for bit-exact checks.
- *   o: (T, C) act in un-rolled token order; lse: (B, nW, heads, L) fp32 log-sum-exp rows.
+ *   o: (T, C) act in un-rolled token order; lse: (2, B, nW, heads, L) fp32 -- plane 0 = log-sum-exp of every softmax row,
+ *   plane 1 = the row's softmax-weighted mean cosine sum_j P_ij cos_ij (zero from back ends whose backward does not use it;
+ *   the tcgen05 backward accumulates d(scale) against it so that the sum is insensitive to the rounding of O).
  * window_attn_bwd: dqkv (T, 3C) act = gradients w.r.t. the *un-normalised* q, k and v;
  *   dscale (heads) += sum dS * cos ; dbias (heads, L, L) += sum_windows dS (nullable).
  *   ws: optional scratch of T*heads floats (the library allocates nothing).  With it the tcgen05 back end runs its

@@ -343,6 +343,8 @@ extern "C" int swinb200_window_attn_fwd(int backend, const void* qkv, int act_dt
     return attn_tcgen05_fwd(qkv, scale, bias, o, lse, B, H, W, C, heads, Wh, Ww, s0, s1, s);
   }
   SWB_CHECK_ARG(backend == SWINB200_GEMM_SIMT, "window_attn_fwd: unknown backend %d", backend);
+  // second plane of `lse` (softmax-weighted mean cosine): not used by this back end's backward, defined as zero
+  SWB_CUDA(cudaMemsetAsync(lse + (size_t)B * g.nW() * heads * Wh * Ww, 0, sizeof(float) * (size_t)B * g.nW() * heads * Wh * Ww, s));
   if (act_dtype == SWINB200_BF16) return launch_fwd<__nv_bfloat16>((const __nv_bfloat16*)qkv, scale, bias, (__nv_bfloat16*)o, lse, g, s);
   if (act_dtype == SWINB200_F32) return launch_fwd<float>((const float*)qkv, scale, bias, (float*)o, lse, g, s);
   SWB_CHECK_ARG(false, "window_attn_fwd: bad act_dtype %d", act_dtype);

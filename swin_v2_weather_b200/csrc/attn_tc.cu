@@ -566,6 +566,8 @@ int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, voi
   }
   if (variant == 3 && ((uintptr_t)qkv % 16 == 0) && g.L * kRowPitch <= (96 / 32) * kCS64)
     return attn_tcgen05_fwd3(qkv, scale, bias, o, lse, g, stream);
+  // the earlier generations do not produce the mean-cosine plane: define it as zero (= un-centred d(scale) in backward)
+  SWB_CUDA(cudaMemsetAsync(lse + (size_t)g.B * g.nW * g.heads * g.L, 0, sizeof(float) * (size_t)g.B * g.nW * g.heads * g.L, stream));
   if (variant == 1) {
     using SM = FwdSmem<96>;
     static bool configured = false;

@@ -53,9 +53,11 @@ struct Bwd3Smem {
   static constexpr int kOffDv = kOffLse + kMaxLP * 4;       // D = <dO, O> per query
   static constexpr int kOffInq = kOffDv + kMaxLP * 4;       // 1 / ||q|| per query slot
   static constexpr int kOffInk = kOffInq + kMaxLP * 4;      // 1 / ||k|| per key slot
-  static constexpr int kOffDot = kOffInk + kMaxLP * 4;      // [2 tile parities][groups][128 rows]: sum_i dS_ij cos_ij partials
-  static constexpr int kOffRed = kOffDot + 2 * kB3Groups * 128 * 4;     // [2][groups][128 rows]: <q^, dQ^> partials
-  static constexpr int kOffDsc = kOffRed + 2 * kB3Groups * 128 * 4;     // per-head d(scale) partial sums of this CTA
+  static constexpr int kOffEc = kOffInk + kMaxLP * 4;       // E_P[cos] per query (second plane of the forward's lse output)
+  static constexpr int kOffDot = kOffEc + kMaxLP * 4;       // [2 tile parities][groups][128 rows]: sum_i dS_ij cos_ij partials
+  static constexpr int kOffRed = kOffDot;                   // <q^, dQ^> partials of the dQ^ epilogue share the buffer: tile t uses
+                                                            // parity (t + ntiles) & 1, never the one the last dK^ epilogue reads
+  static constexpr int kOffDsc = kOffDot + 2 * kB3Groups * 128 * 4;     // per-head d(scale) partial sums of this CTA
   static constexpr int kOffBar = kOffDsc + 128;
   static constexpr int kBytes = kOffBar + 128;
   static_assert(kDS % 512 == 0 && kTile % 512 == 0, "64B-swizzled operand tiles need 512-byte alignment");
@@ -109,6 +111,7 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   float* Dv = reinterpret_cast<float*>(smem + SM::kOffDv);
   float* s_inq = reinterpret_cast<float*>(smem + SM::kOffInq);
   float* s_ink = reinterpret_cast<float*>(smem + SM::kOffInk);
+  float* s_ec = reinterpret_cast<float*>(smem + SM::kOffEc);
   float* dotk = reinterpret_cast<float*>(smem + SM::kOffDot);
   float* red = reinterpret_cast<float*>(smem + SM::kOffRed);
   float* dsc_heads = reinterpret_cast<float*>(smem + SM::kOffDsc);
@@ -164,6 +167,7 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     Dv[n] = 0.f;
     s_inq[n] = 0.f;
     s_ink[n] = 0.f;
+    s_ec[n] = 0.f;
   }
   auto fill_tok = [&](int item, int* tk) {          // compute threads
     const int ww = (item / g.heads) % g.nW;
@@ -181,7 +185,9 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int bb = item / (g.heads * g.nW);
     for (int n = tid; n < L; n += kB3Compute) {
       const int t = tk[n];
-      cp_async4(&lse2[n], lse + (((size_t)bb * g.nW + ww) * g.heads + hd) * L + n);
+      const size_t ri = (((size_t)bb * g.nW + ww) * g.heads + hd) * L + n;
+      cp_async4(&lse2[n], lse + ri);
+      cp_async4(&s_ec[n], lse + (size_t)g.B * g.nW * g.heads * L + ri);
       cp_async4(&Dv[n], Dpre + (size_t)t * g.heads + hd);
       cp_async4(&s_inq[n], inv_norm + (size_t)t * 2 * g.heads + hd);
       cp_async4(&s_ink[n], inv_norm + (size_t)t * 2 * g.heads + g.heads + hd);
@@ -445,6 +451,7 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (last && next_gather) gather(1, vb, tok_next, head_next);   // V served its last MMA: the next item's K^ goes there
         // ---- P^T, dS^T of this thread's key row over the group's query columns ------------------------------------------
         float part = 0.f;                                   // sum_i dS_ij cos_ij
+        float partc = 0.f;                                  // sum_i dS_ij E_P[cos]_i  (d(scale) uses part - partc)
         if (warp_rows && !(dbg & 4)) {
           const int key_label = (jk >= label_split) ? 1 : 0;
           const bool row_exists = jk < LP;
@@ -473,6 +480,11 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                   ds[j] = key_ok ? p * (as_f(pv[hh * 8 + j]) - dd[j]) : 0.f;
                   part = fmaf(ds[j], cosv, part);
                 }
+                {
+                  const float4 e0 = *reinterpret_cast<const float4*>(&s_ec[cb]), e1 = *reinterpret_cast<const float4*>(&s_ec[cb + 4]);
+                  partc = fmaf(ds[0], e0.x, partc); partc = fmaf(ds[1], e0.y, partc); partc = fmaf(ds[2], e0.z, partc); partc = fmaf(ds[3], e0.w, partc);
+                  partc = fmaf(ds[4], e1.x, partc); partc = fmaf(ds[5], e1.y, partc); partc = fmaf(ds[6], e1.z, partc); partc = fmaf(ds[7], e1.w, partc);
+                }
                 tmem_st_32x4(t_lane + kColP + cb / 2, pack8f(pp));             // 8 queries = 4 packed columns of P^T
                 if (row_exists) *reinterpret_cast<uint4*>(sDS + (cb / 8) * SM::kDSCS + jk * 16) = pack8f(ds);
               }
@@ -497,6 +509,7 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 pp[j] = p;
                 ds[j] = (key_ok && qi < L) ? p * (as_f(pv[j]) - Dv[qi]) : 0.f;
                 part = fmaf(ds[j], cosv, part);
+                partc = fmaf(ds[j], s_ec[qi], partc);
                 if (dbias != nullptr && key_ok && qi < L) atomicAdd(dbias + ((size_t)head * L + qi) * L + jk, ds[j]);
               }
               tmem_st_32x4(t_lane + kColP + cb / 2, pack8f(pp));
@@ -506,7 +519,7 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           tmem_st_wait();
         }
         dotk[((u & 1) * kB3Groups + grp) * 128 + r] = part;
-        if (key_ok) dsc_acc += part;        // rows beyond the window read garbage cosines (0 * NaN would poison the sum)
+        if (key_ok) dsc_acc += part - partc;   // rows beyond the window read garbage cosines (0 * NaN would poison the sum)
         fence_proxy_async_smem();       // dS^T (generic-proxy stores) -> visible to the tensor core's async-proxy reads
         tc_fence_before();
         __syncwarp();
@@ -598,12 +611,12 @@ attn_tc_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
           }
         }
-        red[((t & 1) * kB3Groups + grp) * 128 + r] = partq;
+        red[(((t + ntiles) & 1) * kB3Groups + grp) * 128 + r] = partq;
         if (t + 1 < ntiles && slot0 + 128 < L)               // next tile's q^ rows: their L2 round trip runs under the barrier
           fetch_rows(qfetch, qkv + head * D + ecol, tok, slot0 + 128, min(32, L - slot0 - 128));
         named_bar_sync(2, kB3Compute);
         if (warp_has) {
-          const float* rq = red + (t & 1) * kB3Groups * 128 + r;
+          const float* rq = red + ((t + ntiles) & 1) * kB3Groups * 128 + r;
           const float dot = rq[0] + rq[128] + rq[256];                      // <q^_i, dQ^_i>
           const float qs = my_inq[t] * scale;
           uint4 outq[4];

@@ -224,7 +224,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       const float scale_l2 = scale_p[head] * kLog2e;
       mbar_wait(sbar, ph_s, 910); ph_s ^= 1;
       tc_fence_after();
-      float row_sum = 0.f, row_max = -INFINITY;
+      float row_sum = 0.f, row_max = -INFINITY, cos_sum = 0.f;      // cos_sum = sum_j p_j cos_j
       if (warp_rows) {
         if (plain) {
           // Row maximum.  Cosines are bounded by 1, so for scale * log2(e) < 60 the fixed bound scale * 1 is a safe softmax
@@ -266,7 +266,10 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
               for (int j = 0; j < 16; ++j) if (c0 + j >= L) p[j] = 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) row_sum += p[j];
+            for (int j = 0; j < 16; ++j) {
+              row_sum += p[j];
+              cos_sum = fmaf(p[j], as_f(v[j]), cos_sum);
+            }
             tmem_st_32x8(t_s + c0 / 2, pack8(p, 0), pack8(p, 8));
           }
         } else {
@@ -299,12 +302,19 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
               if (((key >= label_split) ? 1 : 0) != my_label) sv += -100.0f * kLog2e;
               p[j] = (key < L && row_ok) ? ex2_approx(sv - row_max) : 0.f;
               row_sum += p[j];
+              if (key < L && row_ok) cos_sum = fmaf(p[j], as_f(v[j]), cos_sum);
             }
             tmem_st_32x8(t_s + c0 / 2, pack8(p, 0), pack8(p, 8));
           }
         }
-        if (row_ok)
-          lse[(((size_t)b * g.nW + w) * g.heads + head) * L + n] = (row_max + log2f(row_sum)) * 0.6931471805599453f;
+        if (row_ok) {
+          const size_t ri = (((size_t)b * g.nW + w) * g.heads + head) * L + n;
+          lse[ri] = (row_max + log2f(row_sum)) * 0.6931471805599453f;
+          // second plane: E_P[cos] of the row.  The backward accumulates d(scale) = sum dS (cos - E_P[cos]); the row sum of dS
+          // is zero in exact arithmetic, so this changes nothing but removes the first-order sensitivity to D = <dO, O>
+          // being formed from the bf16-rounded O.
+          lse[(size_t)g.B * g.nW * g.heads * L + ri] = cos_sum / row_sum;
+        }
         tmem_st_wait();
       }
       tc_fence_before();

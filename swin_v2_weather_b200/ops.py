@@ -272,7 +272,7 @@ def window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, Wh, Ww, s0, s1, mode: C
         backend = attn_backend_for(mode, C, heads, Wh, Ww)
     nW, L = (H // Wh) * (W // Ww), Wh * Ww
     o = torch.empty((T, C), dtype=qkv.dtype, device=qkv.device)
-    lse = torch.empty((B, nW, heads, L), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((2, B, nW, heads, L), dtype=torch.float32, device=qkv.device)   # plane 0: LSE, plane 1: mean cosine
     _lib.call("swinb200_window_attn_fwd", backend, _chk(qkv, "qkv"), _code(qkv.dtype),
               _chk(scale, "scale", torch.float32), _chk(bias, "bias", torch.float32, True), o.data_ptr(), lse.data_ptr(),
               B, H, W, C, heads, Wh, Ww, s0, s1, _stream())
