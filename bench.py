@@ -165,13 +165,13 @@ def gemm_traffic(B, mode):
             f"{d['read_mb_per_launch']:.1f} MB read + {d['write_mb_per_launch']:.1f} MB written per launch)"}
 
 
-def make_model(device, compute_mode="bf16"):
+def make_model(device, compute_mode="bf16", in_chans=None, residual=False):
     from swin_v2_weather_b200.networks.swinv2_global import SwinTransformerV2Cr
     torch.manual_seed(0)
     m = SwinTransformerV2Cr(img_size=CFG["img_size"], patch_size=4, depths=(CFG["depth"],), num_heads=(CFG["num_heads"],),
-                            in_chans=CFG["in_chans"], out_chans=CFG["out_chans"], embed_dim=CFG["embed_dim"],
+                            in_chans=in_chans or CFG["in_chans"], out_chans=CFG["out_chans"], embed_dim=CFG["embed_dim"],
                             img_window_ratio=CFG["window_ratio"], drop_path_rate=CFG["drop_path_rate"],
-                            full_pos_embed=True, rel_pos=False, mlp_ratio=CFG["mlp_ratio"], residual=False,
+                            full_pos_embed=True, rel_pos=False, mlp_ratio=CFG["mlp_ratio"], residual=residual,
                             compute_mode=compute_mode)
     with torch.no_grad():   # the reference zero-inits norm1/2.weight, which makes every block the identity
         g = torch.Generator().manual_seed(1)
@@ -181,11 +181,22 @@ def make_model(device, compute_mode="bf16"):
     return m.to(device).train()
 
 
-def make_loss(device):
+CHANNEL_NAMES_73 = (["u10m", "v10m", "u100m", "v100m", "t2m", "sp", "msl", "tcwv"]      # config/swin.yaml:60-133
+                    + [f"{v}{lev}" for v in "uvztq" for lev in (50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000)])
+
+
+def make_loss(device, config4=False):
     from types import SimpleNamespace
     from swin_v2_weather_b200.utils.losses import LossHandler
     p = SimpleNamespace(n_future=0, img_shape_x=720, img_shape_y=1440, loss='squared geometric l2', channel_weights='none',
                         n_out_channels=73, channel_names=[], out_channels=list(range(73)), dt=1, model_grid_type='equiangular')
+    if config4:   # BASELINE config 4 / SURVEY 8(d): 'auto' channel table x (sigma_global / sigma_dt)^2, synthetic statistics
+        import numpy as np
+        d = tempfile.mkdtemp(prefix="swinb200_stats_")
+        np.save(os.path.join(d, "gs.npy"), np.ones((1, 73, 1, 1), dtype=np.float32))
+        np.save(os.path.join(d, "ts.npy"), np.random.default_rng(7).uniform(0.2, 1.0, size=(1, 73, 1, 1)).astype(np.float32))
+        p.loss, p.channel_weights, p.channel_names = 'weighted absolute temp-std squared geometric l2', 'auto', list(CHANNEL_NAMES_73)
+        p.global_stds_path, p.time_diff_stds_path = os.path.join(d, "gs.npy"), os.path.join(d, "ts.npy")
     return LossHandler(p).to(device).train()
 
 
@@ -202,8 +213,15 @@ def run_ours(args):
     peaks = read_peaks()
     B = args.batch_per_gpu
 
-    model = make_model(dev, args.mode)
-    lossf = make_loss(dev)
+    config4 = args.workload == "config4"
+    model = make_model(dev, args.mode, in_chans=77 if config4 else None, residual=config4)
+    lossf = make_loss(dev, config4)
+    static = None
+    if config4:   # zenith angle per sample + batch-shared one-hot land mask (2) and standardised orography (1): channel groups,
+        gs = torch.Generator().manual_seed(99)          # read in place by the PatchEmbed im2col (no 77-channel concatenation)
+        lsm = torch.nn.functional.one_hot((torch.rand(720, 1440, generator=gs) > 0.7).long()).permute(2, 0, 1).float()[None]
+        oro = torch.randn(1, 1, 720, 1440, generator=gs)
+        static = torch.cat([lsm, (oro - oro.mean()) / (oro.std() + 1e-6)], dim=1).to(dev).contiguous()
     ddp = D.wrap_ddp(model, local)
     params = [p for p in model.parameters()]
 
@@ -213,10 +231,12 @@ def run_ours(args):
     x_res = host_x[:, :, :720].contiguous().to(dev)     # resident copies for the `value` leg (crop as the loaders do)
     t_res = host_t[:, :, :720].contiguous().to(dev)
 
+    zen_res = (torch.rand(B, 1, 720, 1440, generator=gen) * 2 - 1).to(dev) if config4 else None
+
     def step(x, t):
         for p in params:
             p.grad = None
-        pred = ddp(x)
+        pred = ddp((x, zen_res, static)) if config4 else ddp(x)
         loss = lossf(pred, t, x)
         loss.backward()
         return loss
@@ -430,8 +450,12 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode != "fp32" else "f32",
         "data": "synthetic N(0,1) 73x721x1440 fields cropped [:720]; random-init weights (norm1/2.weight ~ N(1,0.1))",
-        "config": {"workload": "swin_73var_geo_depth12: zero_grad + forward + 'squared geometric l2' loss + backward, "
-                               f"batch {B}/GPU, C=768, 8 heads, window 9x18, 64,800 tokens/sample",
+        "config": {"workload": ("swin_73var_geo_depth12 + conditioning (BASELINE config 4): 77 input channels as channel groups "
+                                "(field 73 | zenith 1 | land mask 2 | orography 1), residual skip, 'weighted absolute temp-std squared "
+                                f"geometric l2' loss with the 'auto' channel table, zero_grad + forward + loss + backward, batch {B}/GPU"
+                                if config4 else
+                                "swin_73var_geo_depth12: zero_grad + forward + 'squared geometric l2' loss + backward, "
+                                f"batch {B}/GPU, C=768, 8 heads, window 9x18, 64,800 tokens/sample"),
                    "global_batch": B * world, "parallelism": f"dp{world}", "compute_mode": args.mode,
                    "l2_policy": "per-step working set (>= 19 GB of activations) is far larger than the 126 MB L2",
                    "attention_backend": "tcgen05" if ops_attn_is_tc(args.mode) else "cuda-core"},
@@ -561,6 +585,60 @@ def gpu_eager_samples_per_s(dev, steps=3, warmup=1):
             "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
 
 
+def run_attn_sweep(args):
+    """BASELINE config 5: windowed cosine attention (+ shift mask, with and without the CPB table) at 180 x 360 tokens, C = 768,
+    over window sizes and head counts: forward + backward microseconds (CUDA events), achieved HBM GB/s on the algorithmic
+    bytes (q, k, v, o read / written once forward; q, k, v, o, dO read and dq, dk, dv written backward) and % of the tensor peak
+    on 4 / 10 nW h L^2 d FLOPs.  One JSON line per geometry; `backend` says which kernels ran."""
+    from swin_v2_weather_b200 import _lib, ops
+    from swin_v2_weather_b200._lib import BACKEND_TCGEN05
+    _lib.load()
+    peaks = read_peaks()
+    dev = torch.device("cuda", 0)
+    B, H, W, C = 1, 180, 360, 768
+    T = B * H * W
+    torch.manual_seed(0)
+    qkv0 = torch.randn(T, 3 * C, device=dev).bfloat16()
+    rows = []
+    for window in ((9, 18), (6, 12), (12, 24), (18, 36)):
+        for heads in (4, 8, 12, 16):
+            for shift in ((0, 0), (window[0] // 2, window[1] // 2)):
+                for cpb in (False, True):
+                    L, d = window[0] * window[1], C // heads
+                    rec = {"window": list(window), "heads": heads, "head_dim": d, "shifted": bool(shift[0]), "cpb": cpb}
+                    try:
+                        qkv = qkv0.clone()
+                        inv = ops.qk_normalize_(qkv, C, heads)
+                        scale = torch.full((heads,), 10.0, device=dev)
+                        bias = (0.5 * torch.randn(heads, L, L, device=dev)) if cpb else None
+                        be = ops.attn_backend_for(ops.MODE_BF16, C, heads, *window)
+                        rec["backend"] = "tcgen05" if be == BACKEND_TCGEN05 else "cuda-core"
+                        fwd = lambda: ops.window_attn_fwd(qkv, scale, bias, B, H, W, C, heads, window[0], window[1], shift[0], shift[1], ops.MODE_BF16)
+                        o, lse = fwd()
+                        d_o = torch.randn_like(o)
+                        bwd = lambda: ops.window_attn_bwd(qkv, inv, scale, bias, o, d_o, lse, B, H, W, C, heads, window[0], window[1],
+                                                          shift[0], shift[1], ops.MODE_BF16)
+                        for name, fn, nbytes, nflop in (("fwd", fwd, 4 * T * C * 2, 4.0), ("bwd", bwd, 8 * T * C * 2, 10.0)):
+                            for _ in range(max(1, args.warmup)):
+                                fn()
+                            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                            torch.cuda.synchronize()
+                            ev[0].record()
+                            for _ in range(args.steps):
+                                fn()
+                            ev[1].record()
+                            torch.cuda.synchronize()
+                            us = ev[0].elapsed_time(ev[1]) * 1e3 / args.steps
+                            flops = nflop * (T // L) * heads * L * L * d
+                            rec[name] = {"us": round(us, 1), "hbm_gbs": round(nbytes / us / 1e3, 0), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peaks["hbm"], 3),
+                                         "pct_tc_peak_sustained": round(100 * flops / us / 1e6 / peaks["tf_sust"], 2)}
+                    except Exception as exc:
+                        rec["error"] = f"{type(exc).__name__}: {exc}"[:200]
+                    rows.append(rec)
+                    print(json.dumps(rec), flush=True)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -569,11 +647,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--mode", default="bf16", help="compute mode: bf16 | bf16_simt | fp32")
     ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--workload", default="headline", choices=["headline", "config4"],
+                    help="headline = BASELINE configs[1] (the metric); config4 = conditioning inputs + channel-weighted temp-std loss")
+    ap.add_argument("--sweep", default=None, choices=["attn"], help="attn: BASELINE config 5, the attention kernels over windows / head counts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run one profiled step (for ncu) and exit")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep == "attn":
+        run_attn_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "eager":
         print(json.dumps({"impl": "eager", **gpu_eager_samples_per_s(torch.device("cuda", 0), args.steps, args.warmup)}), flush=True)

@@ -1,4 +1,4 @@
-"""Runs one tcgen05 GEMM case a few times (ncu target):  python tools/gemm_one.py {qkv|gelu|fc2|dgelu|addf32|wgrad}"""
+"""Runs one tcgen05 GEMM case a few times (ncu target):  python tools/gemm_one.py {qkv|qknorm|gelu|fc2|dgelu|addf32|wgrad}"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -11,6 +11,9 @@ case = sys.argv[1]
 if case == "qkv":
     x, w, b = bf(T, C), bf(3 * C, C), torch.randn(3 * C, device="cuda")
     f = lambda: ops.gemm(m, x, 0, w, 0, EPI_BIAS, bias=b)
+elif case == "qknorm":
+    x, w, b = bf(T, C), bf(3 * C, C), torch.randn(3 * C, device="cuda")
+    f = lambda: ops.qkv_projection(m, x, w, b, C, 8)
 elif case == "gelu":
     x, w, b = bf(T, C), bf(HID, C), torch.randn(HID, device="cuda")
     f = lambda: ops.gemm(m, x, 0, w, 0, EPI_BIAS_GELU, bias=b)
