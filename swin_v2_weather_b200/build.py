@@ -46,6 +46,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     headers.append(os.path.join(INCLUDE, "swinb200.h"))
+    headers.append(os.path.join(INCLUDE, "swinb200_debug.h"))
     jobs = []
     objs = []
     for src in sources:

@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "../../include/swinb200.h"
+#include "../../include/swinb200_debug.h"
 
 namespace swinb200 {
 

@@ -8,9 +8,15 @@ from swin_v2_weather_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+HEADERS = ("swinb200.h", "swinb200_debug.h")     # the drop-in boundary, and the bring-up hooks kept out of it
+
+
+def header_text():
+    return "\n".join(open(os.path.join(ROOT, "include", h)).read() for h in HEADERS)
+
+
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "swinb200.h")).read()
-    return sorted(set(re.findall(r"\b(swinb200_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(swinb200_[a-z0-9_]+)\s*\(", header_text())))
 
 
 def test_library_loads_and_exports_header_symbols():
@@ -31,7 +37,7 @@ def test_library_loads_and_exports_header_symbols():
 
 def test_ctypes_prototypes_have_the_arity_of_the_header():
     """A drifting argument list would shift every later pointer by one slot: count them."""
-    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "swinb200.h")).read(), flags=re.S)
+    text = re.sub(r"/\*.*?\*/", "", header_text(), flags=re.S)
     decls = re.findall(r"\bint\s+(swinb200_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
     assert len(decls) >= 17
     for name, args in decls:
