@@ -544,16 +544,14 @@ int attn_make_geom(AttnGeom& g, int B, int H, int W, int C, int heads, int Wh, i
   g.LP = (g.L + 15) / 16 * 16;
   g.nWw = W / Ww;
   g.nW = (H / Wh) * g.nWw;
-  if (g.LP > kMaxLP) {
-    set_error("window_attn (tcgen05): window %dx%d has %d tokens; this kernel handles up to %d", Wh, Ww, g.L, kMaxLP);
-    return SWINB200_ERR_UNSUPPORTED;
-  }
-  if (g.LP < 16 || C / heads != 96) {
-    set_error("window_attn (tcgen05): head_dim %d is not instantiated (96 only)", C / heads);
+  if (!attn_gen_supports(C / heads)) {
+    set_error("window_attn (tcgen05): head_dim %d is not instantiated (48, 64, 96, 128, 192)", C / heads);
     return SWINB200_ERR_UNSUPPORTED;
   }
   return SWINB200_OK;
 }
+// the tuned kernels: head_dim 96 and windows of up to 176 (padded) tokens -- the shipped 9x18 configuration
+static bool attn_is_specialised(const AttnGeom& g) { return g.C / g.heads == 96 && g.LP <= kMaxLP && g.LP >= 16; }
 
 int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, void* o, float* lse, int B, int H, int W, int C,
                      int heads, int Wh, int Ww, int s0, int s1, cudaStream_t stream) {
@@ -562,8 +560,9 @@ int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, voi
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_FWD");
-    variant = e ? atoi(e) : 3;   // 1 = first SS-mode kernel; 2 = two CTAs per SM, cp.async gather; 3 = persistent, TMA boxes, double-buffered
+    variant = e ? atoi(e) : 3;   // 1 = first SS-mode kernel; 2 = two CTAs per SM, cp.async gather; 3 = persistent, TMA boxes, double-buffered; 4 = generic
   }
+  if (!attn_is_specialised(g) || variant == 4) return attn_tcgen05_gen_fwd(qkv, scale, bias, o, lse, g, stream);
   if (variant == 3 && ((uintptr_t)qkv % 16 == 0) && g.L * kRowPitch <= (96 / 32) * kCS64)
     return attn_tcgen05_fwd3(qkv, scale, bias, o, lse, g, stream);
   // the earlier generations do not produce the mean-cosine plane: define it as zero (= un-centred d(scale) in backward)
@@ -1594,8 +1593,10 @@ int attn_tcgen05_bwd(const void* qkv, const float* inv_norm, const float* scale,
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_BWD");
-    variant = e ? atoi(e) : 3;   // 1 = one CTA per (window, head);  2 = persistent two-sweep kernel;  3 = single-pass warp-specialised
+    variant = e ? atoi(e) : 3;   // 1 = one CTA per (window, head);  2 = persistent two-sweep kernel;  3 = single-pass warp-specialised;  4 = generic
   }
+  if (!attn_is_specialised(g) || variant == 4)
+    return attn_tcgen05_gen_bwd(qkv, inv_norm, scale, bias, o, d_o, lse, dqkv, dscale, dbias, ws, g, stream);
   const bool aligned = ((uintptr_t)qkv % 16 == 0) && ((uintptr_t)d_o % 16 == 0);
   if (variant == 3 && ws != nullptr && aligned)
     return attn_tcgen05_bwd3(qkv, inv_norm, scale, bias, o, d_o, lse, dqkv, dscale, dbias, ws, g, stream);
