@@ -11,11 +11,13 @@
 //
 // S-type products take both operands from shared memory (un-swizzled core-matrix layout [16-byte chunk][row][8 elements]: the
 // same bytes serve K-major and MN-major descriptors, so no transposed copy exists anywhere); P / dS are packed to bf16 in place
-// in tensor memory and feed the second product as the TS-mode A operand.  The logits of cosine attention are bounded, so the
-// forward needs no online rescaling: without a bias table the softmax offset is the bound scale*1; with one, a first pass over
-// the key tiles (S products only) finds the exact row maximum.  Y tiles are double-buffered with cp.async groups; two or three
-// CTAs per SM overlap one CTA's softmax with another's gathers.  The roll / window partition is the address computation of
-// the gather (win_token), the shift mask the label predicate of the specialised kernels.
+// in tensor memory and feed the second product as the TS-mode A operand.  The logits of cosine attention are bounded: without
+// a bias table (and scale*log2e < 60) the forward's softmax offset is the bound scale*1 and no maximum is ever taken;
+// otherwise a running maximum is kept per row and the accumulator rows are rescaled in tensor memory only when it grows by more
+// than 2^8 (rare: the tiles of one window see similar logits).  Bias values reach the thread that owns their row through a
+// per-warp shared-memory slab and are fetched one 16-column chunk ahead.  Y tiles are double-buffered with cp.async groups; two
+// to four CTAs per SM overlap one CTA's softmax with another's gathers.  The roll / window partition is the address
+// computation of the gather (win_token), the shift mask the label predicate of the specialised kernels.
 #include "attn_tc.cuh"
 
 namespace swinb200 {
@@ -25,7 +27,7 @@ constexpr int kModeFwd = 0, kModeBwdQ = 1, kModeBwdKV = 2;
 
 __host__ __device__ constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
-template <int D, int KT, int MODE>
+template <int D, int KT, int MODE, bool HAS_BIAS>
 struct GenCfg {
   static constexpr int kChunks = D / 8;
   static constexpr int kNX = (MODE == kModeFwd) ? 1 : 2;
@@ -38,17 +40,20 @@ struct GenCfg {
   static constexpr int kOffTokX = kOffY + 4 * kTileY;
   static constexpr int kOffColA = kOffTokX + 128 * 4;         // [2][KT]  log2-domain LSE of the streamed query rows (backward B)
   static constexpr int kOffColB = kOffColA + 2 * KT * 4;      // [2][KT]  D = <dO, O> of the streamed query rows
-  static constexpr int kOffBar = kOffColB + 2 * KT * 4;
+  static constexpr int kOffBias = kOffColB + 2 * KT * 4;      // [4 warps][32 rows][20] bias pieces on their way to their rows (fwd / A)
+  static constexpr int kOffBar = kOffBias + ((MODE == kModeBwdKV || !HAS_BIAS) ? 0 : 4 * 32 * 20 * 4);
   static constexpr int kBytes = kOffBar + 64;
   static constexpr int kStagePitch = D * 2 + 16;              // output rows parked in the (dead) Y buffers
   static constexpr int kColS = 0, kColDP = KT;
   static constexpr int kColAcc0 = (MODE == kModeFwd) ? KT : 2 * KT;
   static constexpr int kColAcc1 = kColAcc0 + D;
-  static constexpr int kTmemCols = pow2_cols(kColAcc0 + ((MODE == kModeBwdKV) ? 2 : 1) * D);
+  static constexpr int kColAdd = kColAcc0 + D;               // forward: log2-domain addend (bias + mask) of the current tile
+  static constexpr int kColsUsed = kColAcc0 + ((MODE == kModeBwdKV) ? 2 : 1) * D + ((MODE == kModeFwd && HAS_BIAS) ? KT : 0);
+  static constexpr int kTmemCols = pow2_cols(kColsUsed);
   static_assert(D % 16 == 0 && D >= 16 && D <= 256, "head_dim");
   static_assert(KT % 16 == 0 && KT <= 128, "streamed tile");
   static_assert(128 * kStagePitch <= 4 * kTileY, "staging fits the Y buffers");
-  static_assert(kColAcc0 + ((MODE == kModeBwdKV) ? 2 : 1) * D <= 512, "tensor memory");
+  static_assert(kColsUsed <= 512, "tensor memory");
   static_assert(kBytes <= 227 * 1024, "shared memory");
 };
 
@@ -65,12 +70,19 @@ struct GenArgs {
   float* dbias;                  // (heads, L, L) or null
 };
 
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+      "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-template <int D, int KT, int MODE>
+template <int D, int KT, int MODE, bool HAS_BIAS>
 __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const AttnGeom g) {
-  using CF = GenCfg<D, KT, MODE>;
+  using CF = GenCfg<D, KT, MODE, HAS_BIAS>;
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr float kLn2 = 0.6931471805599453f;
   constexpr float kMaskL2 = -100.0f * kLog2e;
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
     label_split = first_row <= 0 ? 0 : (first_row >= g.Wh ? L : first_row * g.Ww);
   }
   const bool use_mask = label_split > 0 && label_split < L;
-  const bool plain = (a.bias == nullptr) && !use_mask;
+  const bool plain = !HAS_BIAS && !use_mask;
 
   const int nx = xt * 128 + tid;                 // this thread's stationary slot (query for fwd / A, key for B) == TMEM lane
   const bool row_ok = nx < L;
@@ -174,13 +186,12 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
 
   const float scale = a.scale[head];
   const float scale_l2 = scale * kLog2e;
-  // forward: the bound scale*1 on the logits replaces the row maximum when nothing is added to them
-  const bool need_max = (MODE == kModeFwd) && !((a.bias == nullptr) && scale_l2 < 60.f);
-  const int npass = need_max ? 2 : 1;
-  const int total = npass * nY;
-  auto ops_of = [&](int u) { return (need_max && u < nY) ? 1 : 3; };
+  // forward: the bound scale*1 on the logits replaces the row maximum when nothing is added to them; otherwise a running
+  // maximum, re-based (accumulator rows rescaled in tensor memory) only when it grows by more than 2^8
+  const bool bounded = !HAS_BIAS && scale_l2 < 60.f;
+  const int total = nY;
 
-  gather_y(0, 0, ops_of(0));
+  gather_y(0, 0, 3);
   cp_async_commit();
 
   // per-row terms of backward A
@@ -190,7 +201,46 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
     my_mc = a.lse[(size_t)g.B * g.nW * g.heads * L + row_base + nx];
     my_D = a.Dpre[(size_t)tokX[tid] * g.heads + head];
   }
-  const float* brow = (MODE != kModeBwdKV && a.bias != nullptr && row_ok) ? a.bias + ((size_t)head * L + nx) * L : nullptr;
+  // bias[query][key .. key+15] for this thread's query: a warp instruction reading 32 different rows costs 32 L1 tag
+  // cycles, so the warp fetches the 32 x 16 block as 16 loads of two 64-byte row pieces each and redistributes it through
+  // a 2.5 KB slab (row pitch 80 B: the 16-byte reads are conflict-free)
+  // Values are fetched one 16-column chunk ahead (across tile boundaries too), so the L2 latency hides behind the arithmetic
+  // of the current chunk and the waits between tiles.  Backward B (thread = key) reads bias[query][key] with consecutive
+  // lanes on consecutive keys: coalesced as it is, prefetched the same way.
+  float* sbias = reinterpret_cast<float*>(smem + CF::kOffBias) + warp * (32 * 20);
+  float nb[16];
+  auto bias_fetch = [&](int y0_) {               // y0_ = first streamed slot of the chunk; out-of-range chunks fetch nothing
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (MODE == kModeBwdKV) {
+        const int qi = y0_ + i;
+        nb[i] = (row_ok && qi < L) ? __ldg(a.bias + ((size_t)head * L + qi) * L + nx) : 0.f;
+      } else {
+        const int row = 2 * i + (lane >> 4), col = lane & 15;
+        const int q = xt * 128 + warp * 32 + row, key = y0_ + col;
+        nb[i] = (q < L && key < L) ? __ldg(a.bias + ((size_t)head * L + q) * L + key) : 0.f;
+      }
+    }
+  };
+  auto bias_take = [&](float (&bv)[16]) {        // the chunk fetched last, as log2-domain addends of this thread's 16 columns
+    if (MODE == kModeBwdKV) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bv[j] = nb[j] * kLog2e;
+    } else {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sbias[(2 * i + (lane >> 4)) * 20 + (lane & 15)] = nb[i] * kLog2e;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(&bv[j]) = *reinterpret_cast<const float4*>(sbias + lane * 20 + j);
+    }
+  };
+  // first slot of the chunk after (tile u, column c0) in processing order
+  auto next_chunk = [&](int u, int c0) {
+    if (c0 + 16 < KT) return u * KT + c0 + 16;
+    return (u + 1 >= total) ? L : (u + 1) * KT;
+  };
+  if (HAS_BIAS) bias_fetch(0);
 
   tc_fence_before();
   __syncthreads();
@@ -206,10 +256,9 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
   float row_max = -INFINITY, row_sum = 0.f, cos_sum = 0.f, dsc_acc = 0.f;
 
   for (int u = 0; u < total; ++u) {
-    const int t = (u >= nY) ? u - nY : u;
+    const int t = u;
     const int buf = u & 1;
-    const bool max_pass = need_max && u < nY;
-    if (u + 1 < total) gather_y((u + 1 >= nY) ? u + 1 - nY : u + 1, buf ^ 1, ops_of(u + 1));
+    if (u + 1 < total) gather_y(u + 1, buf ^ 1, 3);
     cp_async_commit();
     cp_async_wait_1();                           // everything but the group just committed: tile u (and X) have landed
     fence_proxy_async_smem();
@@ -237,43 +286,73 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
     const int y_base = t * KT;                   // first streamed slot of this tile
     const bool ragged = y_base + KT > L;
     if (MODE == kModeFwd) {
-      const float off = need_max ? row_max : scale_l2;
+      if (!bounded) {
+        // sub-pass 1: the addend (bias + mask, -inf for pad keys) of every column goes to scratch columns, tile maximum on the way
+        float tile_max = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < KT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_lane + CF::kColS + c0, v);
-        tmem_ld_wait();
-        float sv[16];
-        if (plain) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sv[j] = as_f(v[j]) * scale_l2;
-        } else {
+        for (int c0 = 0; c0 < KT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_lane + CF::kColS + c0, v);
+          float bv[16];
+          if (HAS_BIAS) {
+            bias_take(bv);
+            bias_fetch(next_chunk(u, c0));
+          }
+          tmem_ld_wait();
+          float add[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int key = y_base + c0 + j;
-            float s = as_f(v[j]) * scale_l2;
-            if (brow != nullptr && key < L) s = fmaf(brow[key], kLog2e, s);
-            if (use_mask && ((key >= label_split) ? 1 : 0) != x_label) s += kMaskL2;
-            sv[j] = s;
+            float ad = HAS_BIAS ? bv[j] : 0.f;
+            if (use_mask && ((key >= label_split) ? 1 : 0) != x_label) ad += kMaskL2;
+            if (ragged && key >= L) ad = -INFINITY;
+            add[j] = ad;
+            tile_max = fmaxf(tile_max, fmaf(as_f(v[j]), scale_l2, ad));
           }
+          if (HAS_BIAS) tmem_st_32x16(t_lane + CF::kColAdd + c0, add);      // without a table the addend is recomputed below
         }
-        if (max_pass) {
+        if (HAS_BIAS) tmem_st_wait();
+        const bool grow = tile_max > row_max + 8.f;            // first tile: row_max = -inf
+        if (__any_sync(0xffffffffu, grow)) {
+          const float f = grow ? ex2_approx(row_max - tile_max) : 1.f;
+          if (t > 0) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < D; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld_32x16(t_lane + CF::kColAcc0 + c0, v);
+              tmem_ld_wait();
+              float r16[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (!ragged || y_base + c0 + j < L) row_max = fmaxf(row_max, sv[j]);
-        } else {
-          float p[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            p[j] = ex2_approx(sv[j] - off);
-            if (ragged && y_base + c0 + j >= L) p[j] = 0.f;
-            row_sum += p[j];
-            cos_sum = fmaf(p[j], as_f(v[j]), cos_sum);
+              for (int j = 0; j < 16; ++j) r16[j] = as_f(v[j]) * f;
+              tmem_st_32x16(t_lane + CF::kColAcc0 + c0, r16);
+            }
           }
-          tmem_st_32x8(t_lane + CF::kColS + c0 / 2, pack8(p, 0), pack8(p, 8));     // keys [c0, c0+16) -> 8 packed columns, already consumed
+          row_sum *= f;
+          cos_sum *= f;
+          if (grow) row_max = tile_max;
         }
       }
-      if (max_pass) continue;                     // the next S product waits for the barrier at the top of the loop
+      const float off = bounded ? scale_l2 : row_max;
+#pragma unroll 1
+      for (int c0 = 0; c0 < KT; c0 += 16) {
+        uint32_t v[16], ad[16];
+        tmem_ld_32x16(t_lane + CF::kColS + c0, v);
+        if (HAS_BIAS) tmem_ld_32x16(t_lane + CF::kColAdd + c0, ad);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int key = y_base + c0 + j;
+          float s = as_f(v[j]) * scale_l2;
+          if (HAS_BIAS) s += as_f(ad[j]);                       // bias + mask, -inf for pad keys
+          else if (use_mask && ((key >= label_split) ? 1 : 0) != x_label) s += kMaskL2;
+          p[j] = ex2_approx(s - off);
+          if (!HAS_BIAS && ragged && key >= L) p[j] = 0.f;
+          row_sum += p[j];
+          cos_sum = fmaf(p[j], as_f(v[j]), cos_sum);
+        }
+        tmem_st_32x8(t_lane + CF::kColS + c0 / 2, pack8(p, 0), pack8(p, 8));     // keys [c0, c0+16) -> 8 packed columns, already consumed
+      }
     } else if (MODE == kModeBwdQ) {
       float dsc_tile = 0.f;
 #pragma unroll 1
@@ -281,6 +360,11 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
         uint32_t v[16], dp[16];
         tmem_ld_32x16(t_lane + CF::kColS + c0, v);
         tmem_ld_32x16(t_lane + CF::kColDP + c0, dp);
+        float bv[16];
+        if (HAS_BIAS) {
+          bias_take(bv);
+          bias_fetch(next_chunk(u, c0));
+        }
         tmem_ld_wait();
         float ds[16];
 #pragma unroll
@@ -289,7 +373,7 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
           const float cosv = as_f(v[j]);
           float s = cosv * scale_l2;
           if (!plain) {
-            if (brow != nullptr && key < L) s = fmaf(brow[key], kLog2e, s);
+            if (HAS_BIAS) s += bv[j];
             if (use_mask && ((key >= label_split) ? 1 : 0) != x_label) s += kMaskL2;
           }
           const float p = ex2_approx(s - my_lse2);               // pad query rows: lse = +inf -> 0
@@ -315,6 +399,11 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
           *reinterpret_cast<float4*>(&ls[j]) = *reinterpret_cast<const float4*>(cA + c0 + j);
           *reinterpret_cast<float4*>(&dd[j]) = *reinterpret_cast<const float4*>(cB + c0 + j);
         }
+        float bv[16];
+        if (HAS_BIAS) {
+          bias_take(bv);
+          bias_fetch(next_chunk(u, c0));
+        }
         tmem_ld_wait();
         float pp[16], ds[16];
 #pragma unroll
@@ -322,7 +411,7 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
           const int qi = y_base + c0 + j;
           float s = as_f(v[j]) * scale_l2;
           if (!plain) {
-            if (a.bias != nullptr && row_ok && qi < L) s = fmaf(a.bias[((size_t)head * L + qi) * L + nx], kLog2e, s);
+            if (HAS_BIAS) s += bv[j];
             if (use_mask && ((qi >= label_split) ? 1 : 0) != x_label) s += kMaskL2;
           }
           const float p = row_ok ? ex2_approx(fmaf(-ls[j], kLog2e, s)) : 0.f;     // pad queries: lse = +inf -> 0
@@ -427,7 +516,7 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
 
   if (MODE == kModeFwd) {
     if (row_ok) {
-      const float off = need_max ? row_max : scale_l2;
+      const float off = bounded ? scale_l2 : row_max;
       a.lse[row_base + nx] = (off + log2f(row_sum)) * kLn2;
       a.lse[(size_t)g.B * g.nW * g.heads * L + row_base + nx] = cos_sum / row_sum;
     }
@@ -462,12 +551,12 @@ __global__ void __launch_bounds__(128) attn_gen_kernel(const GenArgs a, const At
   }
 }
 
-template <int D, int KT, int MODE>
-int launch_gen(const GenArgs& a, const AttnGeom& g, cudaStream_t stream) {
-  using CF = GenCfg<D, KT, MODE>;
+template <int D, int KT, int MODE, bool HAS_BIAS>
+int launch_gen_b(const GenArgs& a, const AttnGeom& g, cudaStream_t stream) {
+  using CF = GenCfg<D, KT, MODE, HAS_BIAS>;
   static bool configured = false;
   if (!configured) {
-    SWB_CUDA(cudaFuncSetAttribute(attn_gen_kernel<D, KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kBytes));
+    SWB_CUDA(cudaFuncSetAttribute(attn_gen_kernel<D, KT, MODE, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kBytes));
     configured = true;
   }
   const long long ctas = (long long)g.B * g.nW * g.heads * ((g.L + 127) / 128);
@@ -475,9 +564,13 @@ int launch_gen(const GenArgs& a, const AttnGeom& g, cudaStream_t stream) {
     set_error("window_attn (tcgen05): %lld CTAs exceed the grid limit", ctas);
     return SWINB200_ERR_UNSUPPORTED;
   }
-  attn_gen_kernel<D, KT, MODE><<<(unsigned)ctas, 128, CF::kBytes, stream>>>(a, g);
+  attn_gen_kernel<D, KT, MODE, HAS_BIAS><<<(unsigned)ctas, 128, CF::kBytes, stream>>>(a, g);
   SWB_LAUNCH_CHECK();
   return SWINB200_OK;
+}
+template <int D, int KT, int MODE>
+int launch_gen(const GenArgs& a, const AttnGeom& g, cudaStream_t stream) {
+  return a.bias != nullptr ? launch_gen_b<D, KT, MODE, true>(a, g, stream) : launch_gen_b<D, KT, MODE, false>(a, g, stream);
 }
 
 template <int MODE>
