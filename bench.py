@@ -99,7 +99,7 @@ class KernelTimer:
               "swinb200_ln_residual_fwd": "ln_fwd", "swinb200_ln_residual_bwd": "ln_bwd", "swinb200_colsum": "colsum",
               "swinb200_patchify": "patchify", "swinb200_unpatchify": "unpatchify", "swinb200_latw_l2_fwd": "loss",
               "swinb200_latw_l2_bwd": "loss", "swinb200_transpose_f32": "transpose", "swinb200_pos_embed_grad": "transpose",
-              "swinb200_cast_f32_to_bf16": "cast"}
+              "swinb200_cast_f32_to_bf16": "cast", "swinb200_linear_ln_residual": "gemm_ln"}
 
     def __init__(self):
         self.records = []   # (family, flops, bytes, start_event, end_event)
@@ -121,6 +121,13 @@ class KernelTimer:
                 Bq, H, W, C, heads, Wh, Ww = args[13:20]
             L = Wh * Ww
             flops = (4.0 if fam == "attn_fwd" else 10.0) * Bq * (H // Wh) * (W // Ww) * heads * L * L * (C // heads)
+        if fam == "gemm_ln":
+            # proj / fc2 + LayerNorm + residual in one kernel: GEMM operands + z (bf16) + x_in, x_out (fp32) + bf16 shadow
+            M, N, K = args[1], args[2], args[3]
+            fam = "gemm_tcgen05"
+            flops = 2.0 * M * N * K
+            bytes_ = 2.0 * (M * K + N * K) + 12.0 * M * N
+            variant = f"M{M}_N{N}_K{K}_a0b0_bias_ln_residual"
         if fam == "gemm":
             backend, M, N, K = args[0], args[1], args[2], args[3]
             fam = "gemm_tcgen05" if backend == 1 else "gemm_simt"

@@ -36,6 +36,8 @@ enum {
                                    (= head_dim) columns of the q and k thirds is divided by max(||.||_2, 1e-12)
                                    (F.normalize, swinv2_global.py:185,304); D2 (M, 2*N/(3*head_dim)) fp32 receives the
                                    reciprocal norms.  tcgen05 back end, head_dim 96 only.               (D: act)  */
+  SWINB200_EPI_BIAS_LN = 6,   /* internal to swinb200_linear_ln_residual: D = acc + bias, then LayerNorm + residual of
+                                   every finished 128-row block inside the epilogue                      (D: act)  */
 };
 /* GEMM back ends */
 enum { SWINB200_GEMM_SIMT = 0, SWINB200_GEMM_TCGEN05 = 1 };
@@ -96,6 +98,20 @@ int swinb200_gemm(int backend, int M, int N, int K, const void* A, int a_major, 
                   int b_major, int ldb, int in_dtype, int epilogue, const float* bias, void* D, int ldd,
                   void* D2, const void* aux, int ld_aux, int out_dtype, int accumulate, int split_k,
                   void* stream);
+
+/* ---- Linear + LayerNorm + DropPath + residual in one kernel -----------------------------------------
+ * z = A W^T + bias (stored, bf16: the backward needs it) ; u = LN_N(z) * gamma + beta (* sample_scale[row /
+ * rows_per_sample] if given) ; x_out = x_in + u ; xb_out = bf16(x_out) ; stats[row] = (mean, rstd)
+ *   == `x = x + self.drop_path(self.norm1(self.attn.proj(...)))` and `x = x + self.drop_path(self.norm2(self.mlp.fc2(...)))`
+ *   (swinv2_global.py:199/319 + 490, timm Mlp.fc2 + 494): the LayerNorm + residual run inside the GEMM epilogue -- the
+ *   CTA that completes the last column tile of a 128-row block normalises that block while the tensor cores work on the
+ *   next tiles.  tcgen05 back end, bf16 operands, N = 768 (three 256-column tiles per row); other shapes / back ends
+ *   return SWINB200_ERR_UNSUPPORTED and the caller runs swinb200_gemm(EPI_BIAS) + swinb200_ln_residual_fwd.
+ *   counters: n_counters >= ceil(M / 128) ints, zero on entry; the kernel leaves them zero. */
+int swinb200_linear_ln_residual(int backend, int M, int N, int K, const void* A, int lda, const void* W, int ldw,
+                                const float* bias, void* z, int ldz, const float* x_in, const float* gamma,
+                                const float* beta, const float* sample_scale, float* x_out, void* xb_out, float* stats,
+                                int rows_per_sample, float eps, int* counters, int n_counters, void* stream);
 
 /* ---- LayerNorm + residual (post-norm) -------------------------------------------------------------
  * fwd:  u = LN_C(z) * gamma + beta  (+ pos[t % rows_per_sample, c] if pos)  (* sample_scale[b] if given)

@@ -45,6 +45,21 @@ inline int sm_count() {
   return n;
 }
 
+// LayerNorm + DropPath scale + residual operands of the fused proj / fc2 epilogue (SWINB200_EPI_BIAS_LN, gemm_tc.cu)
+struct GemmLnFuse {
+  const float* x_in;
+  const float* gamma;
+  const float* beta;
+  const float* sample_scale;   // may be null
+  float* x_out;
+  void* xb_out;
+  float* stats;
+  int* counters;
+  int n_counters;
+  int rows_per_sample;
+  float eps;
+};
+
 // ---- activation storage type helpers ------------------------------------------------------------
 template <typename T> struct Act;
 template <> struct Act<float> {

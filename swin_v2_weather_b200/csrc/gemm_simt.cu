@@ -114,7 +114,7 @@ static int launch_simt(int M, int N, int K, const T* A, int a_major, int lda, co
 
 int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
                  const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const GemmLnFuse* ln = nullptr);
 
 }  // namespace swinb200
 
@@ -153,4 +153,20 @@ extern "C" int swinb200_gemm(int backend, int M, int N, int K, const void* A, in
   if (in_dtype == SWINB200_F32)
     return launch_simt<float>(M, N, K, (const float*)A, a_major, lda, (const float*)B, b_major, ldb, epilogue, bias, D, ldd, D2, aux, ld_aux, accumulate, s);
   SWB_CHECK_ARG(false, "gemm: bad in_dtype %d", in_dtype);
+}
+
+extern "C" int swinb200_linear_ln_residual(int backend, int M, int N, int K, const void* A, int lda, const void* W, int ldw,
+                                           const float* bias, void* z, int ldz, const float* x_in, const float* gamma,
+                                           const float* beta, const float* sample_scale, float* x_out, void* xb_out, float* stats,
+                                           int rows_per_sample, float eps, int* counters, int n_counters, void* stream) {
+  SWB_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear_ln_residual: bad shape M=%d N=%d K=%d", M, N, K);
+  SWB_CHECK_ARG(A && W && z && x_in && gamma && beta && x_out && xb_out && stats && counters, "linear_ln_residual: null pointer");
+  SWB_CHECK_ARG(lda >= K && ldw >= K && ldz >= N && rows_per_sample > 0, "linear_ln_residual: leading dimension too small");
+  if (backend != SWINB200_GEMM_TCGEN05 || N != 768) {
+    set_error("linear_ln_residual: the fused epilogue is a tcgen05 / bf16 kernel for 768 output channels; "
+              "run swinb200_gemm(EPI_BIAS) + swinb200_ln_residual_fwd for backend %d, N = %d", backend, N);
+    return SWINB200_ERR_UNSUPPORTED;
+  }
+  GemmLnFuse ln{x_in, gamma, beta, sample_scale, x_out, xb_out, stats, counters, n_counters, rows_per_sample, eps};
+  return gemm_tcgen05(M, N, K, A, 0, lda, W, 0, ldw, SWINB200_EPI_BIAS_LN, bias, z, ldz, nullptr, nullptr, 0, 0, 1, (cudaStream_t)stream, &ln);
 }

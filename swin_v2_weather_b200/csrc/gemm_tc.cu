@@ -45,23 +45,41 @@ struct GemmTcParams {
   int debug;       // bring-up timing experiments (SWINB200_GEMM_DEBUG): 1 = no staging wait, 2 = no store, 4 = no tmem ld wait
   int atomic_out;  // EPI_F32: 1 = TMA reduce-add (split-K / accumulate), 0 = plain TMA store
   int num_m_tiles, num_n_tiles, split_k, kb_total, kb_per_split;
+  // BIAS_LN: post-norm LayerNorm + DropPath scale + residual add of finished 128-row blocks, inside the epilogue
+  const float* ln_x_in;           // (M, N) fp32 residual stream
+  const float* ln_gamma;          // (N)
+  const float* ln_beta;           // (N)
+  const float* ln_sample_scale;   // (M / rows_per_sample) DropPath multipliers or null
+  float* ln_x_out;                // (M, N) fp32
+  __nv_bfloat16* ln_xb_out;       // (M, N) bf16 shadow
+  float* ln_stats;                // (M, 2) mean, rstd
+  const __nv_bfloat16* ln_z;      // D as the epilogue warps re-read it (ldd pitch)
+  int ln_ldz;
+  int* ln_counters;               // one per 128-row block, zero on entry and on exit
+  int ln_rows_per_sample;
+  float ln_eps;
+  int ln_slices;                  // 32-row LayerNorm slices a CTA may run per tile boundary
 };
 
 // PAIR: two CTAs of a cluster (two SMs) share one 256 x BN tile: tcgen05.mma.cta_group::2 reads the A rows and one half
 // of the B columns from each CTA's shared memory, so every SM stages (and the tensor core re-reads) a third less operand
 // data per k-step and the smem ring gets deeper.
-template <int BN, bool PAIR = false>
+template <int BN, bool PAIR = false, bool LN = false>
 struct GemmCfg {
   static constexpr int kStageA = GBM * GBK * 2;
   static constexpr int kStageB = (PAIR ? BN / 2 : BN) * GBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = PAIR ? 5 : ((BN >= 192) ? 3 : 5);   // 5 x 32 KB stages + 64 KB of staging fill the SM
+  static constexpr int kStages = LN ? (PAIR ? 4 : 3) : (PAIR ? 5 : ((BN >= 192) ? 3 : 5));   // 5 x 32 KB stages + 64 KB of staging fill the SM; BIAS_LN: 4 stages, so that 60 KB of L1 remain for the row loads of the LayerNorm pass
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  // BIAS_LN keeps gamma / beta (up to 1024 channels each) in shared memory and pays for them with the second staging buffer
+  static constexpr int kSB = LN ? 1 : kStagingBufs;
   static constexpr int kOffStaging = kStages * kStage;
-  static constexpr int kOffBars = kOffStaging + kEpiGroups * 4 * kStagingBufs * kStagingBytes;
+  static constexpr int kOffBars = kOffStaging + kEpiGroups * 4 * kSB * kStagingBytes;
   static constexpr int kOffBias = kOffBars + 256;
   static constexpr int kOffSsq = kOffBias + kBiasBytes;               // BIAS_QKNORM: [2 tile parities][BN/32 pieces][128 rows] partial sums of squares
-  static constexpr int kSmem = kOffSsq + ((BN == 192) ? 2 * (BN / 32) * GBM * 4 : 0);
+  static constexpr int kOffLn = kOffSsq + ((BN == 192) ? 2 * (BN / 32) * GBM * 4 : 0);   // BIAS_LN: gamma[1024], beta[1024], flag
+  static constexpr int kOffLnX = kOffLn + 2 * 1024 * 4 + 64;                          // BIAS_LN: one fp32 row of x_in per epilogue warp (prefetch)
+  static constexpr int kSmem = LN ? kOffLnX + kEpiGroups * 4 * 768 * 4 : kOffLn;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
@@ -236,7 +254,9 @@ template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const GemmTcParams p) {
-  using Cfg = GemmCfg<BN, PAIR>;
+  constexpr bool kLn = (EPI == SWINB200_EPI_BIAS_LN);
+  using Cfg = GemmCfg<BN, PAIR, kLn>;
+  constexpr int kSB = Cfg::kSB;                        // staging buffers per epilogue warp
   constexpr int BNL = PAIR ? BN / 2 : BN;              // B columns staged by this CTA
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u; // 0 = leader (issues the MMAs), 1 = peer
   const int cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;   // persistent stride in tiles
@@ -287,6 +307,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
+  if (kLn) {
+    float* sg = reinterpret_cast<float*>(smem + Cfg::kOffLn);
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) {
+      sg[i] = __ldg(p.ln_gamma + i);
+      sg[1024 + i] = __ldg(p.ln_beta + i);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -415,10 +442,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;     // row inside the tile
     const int gt = threadIdx.x & 127;      // thread index inside the group (group g = warps 4g .. 4g+3)
-    unsigned char* stg_base = smem + Cfg::kOffStaging + ew * kStagingBufs * kStagingBytes;
+    unsigned char* stg_base = smem + Cfg::kOffStaging + ew * kSB * kStagingBytes;
     uint32_t stg_sel = 0;                  // staging buffer of the next piece
     // Each warp stages and stores its own 32 rows: no cross-warp barrier sits between tcgen05.ld and the TMA store.
-    constexpr bool kBiasEpi = (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU || EPI == SWINB200_EPI_BIAS_QKNORM);
+    constexpr bool kBiasEpi = (EPI == SWINB200_EPI_BIAS || EPI == SWINB200_EPI_BIAS_GELU || EPI == SWINB200_EPI_BIAS_QKNORM || kLn);
     constexpr int kChunksPerGroup = (kNumChunks + kEpiGroups - 1) / kEpiGroups;
     constexpr int kBiasSlots = kChunksPerGroup * kChunkCols;
     static_assert(!kBiasEpi || kBiasSlots <= 64, "bias slices must fit");
@@ -426,6 +453,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_bias = kBiasEpi && p.bias != nullptr;
     const int mrow0 = quarter * 32;        // first tile row of this warp
     int qk_tiles = 0;                      // BIAS_QKNORM: tiles that exchanged norms so far
+    // ---- BIAS_LN: x_out = x_in + s * (LN(z) gamma + beta) for a 128-row block whose last column tile has just landed ----------
+    // Every CTA counts the tiles it has *completely* written (all 16 warps' TMA stores finished) per 128-row block; the CTA
+    // that brings a block's count to num_n_tiles re-reads the block's bf16 rows of z (L2-hot, written by up to three SMs)
+    // and runs the row routine of ln_residual_fwd_kernel, warp per row, while the MMA warp is already filling the next
+    // accumulators.  The bookkeeping runs one tile behind so that no warp ever waits for its own stores to drain.
+    int ln_prev_blk = -1;
+    volatile int* ln_flag = reinterpret_cast<volatile int*>(smem + Cfg::kOffLn + 2 * 1024 * 4);
+    auto ln_rows = [&](int blk, int r_begin, int r_end) {
+      constexpr int NK = 6;                  // 768 channels: lane owns 4 channels at lane*4 + 128*k (host checks N == 768), so
+                                             // every fp32 access is one whole 512-byte line per warp and every bf16 access 256 bytes
+      const float* sg = reinterpret_cast<const float*>(smem + Cfg::kOffLn);
+      const float invC = 1.0f / (float)p.N;
+      // Two rows are in flight per warp: while row i is normalised, row i+1's x_in streams into the warp's shared-memory
+      // row (cp.async: no registers) and its z sits in 12 registers.  Every lane reads back exactly the bytes it copied.
+      float* xrow = reinterpret_cast<float*>(smem + Cfg::kOffLnX) + ew * 768;
+      auto fetch = [&](int row, uint2 (&zn)[NK]) {
+        if (row < p.M) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const int c = lane * 4 + k * 128;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xrow + c)), "l"(p.ln_x_in + (size_t)row * p.N + c) : "memory");
+            zn[k] = __ldcg(reinterpret_cast<const uint2*>(p.ln_z + (size_t)row * p.ln_ldz + c));
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      uint2 zn[NK];
+      fetch(blk * GBM + r_begin + ew, zn);
+      for (int rr = r_begin + ew; rr < r_end; rr += 4 * kEpiGroups) {
+        const int row = blk * GBM + rr;
+        if (row >= p.M) break;
+        uint2 zq[NK];
+        float4 xi[NK];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          zq[k] = zn[k];
+          xi[k] = *reinterpret_cast<const float4*>(xrow + lane * 4 + k * 128);
+        }
+        if (rr + 4 * kEpiGroups < r_end) fetch(row + 4 * kEpiGroups, zn);
+        float v[NK][4];
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          unpack_bf16x2(zq[k].x, v[k][0], v[k][1]);
+          unpack_bf16x2(zq[k].y, v[k][2], v[k][3]);
+          sum += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+        }
+        const float mean = warp_sum(sum) * invC;
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d = v[k][e] - mean;
+            sq = fmaf(d, d, sq);
+          }
+        const float rstd = rsqrtf(warp_sum(sq) * invC + p.ln_eps);
+        const float sc = p.ln_sample_scale ? __ldg(p.ln_sample_scale + row / p.ln_rows_per_sample) : 1.0f;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const int c = lane * 4 + k * 128;
+          const float4 g4 = *reinterpret_cast<const float4*>(sg + c);
+          const float4 b4 = *reinterpret_cast<const float4*>(sg + 1024 + c);
+          float4 r;
+          r.x = fmaf((v[k][0] - mean) * rstd, g4.x, b4.x) * sc + xi[k].x;
+          r.y = fmaf((v[k][1] - mean) * rstd, g4.y, b4.y) * sc + xi[k].y;
+          r.z = fmaf((v[k][2] - mean) * rstd, g4.z, b4.z) * sc + xi[k].z;
+          r.w = fmaf((v[k][3] - mean) * rstd, g4.w, b4.w) * sc + xi[k].w;
+          if (!(p.debug & 16)) {
+            *reinterpret_cast<float4*>(p.ln_x_out + (size_t)row * p.N + c) = r;
+            uint2 pk;
+            pk.x = pack_bf16x2(r.x, r.y);
+            pk.y = pack_bf16x2(r.z, r.w);
+            *reinterpret_cast<uint2*>(p.ln_xb_out + (size_t)row * p.N + c) = pk;
+          }
+        }
+        if (lane == 0) {
+          p.ln_stats[2 * (size_t)row] = mean;
+          p.ln_stats[2 * (size_t)row + 1] = rstd;
+        }
+      }
+    };
+    // Finished blocks wait in a small queue and are normalised in slices of 32 rows, at most p.ln_slices per tile boundary:
+    // the LayerNorm's HBM traffic is spread over the whole kernel instead of arriving in bursts that outlast the two tiles
+    // the MMA warp can run ahead.  Queue indices are replicated in every warp (all warps see the same flags); only the
+    // block ids live in shared memory.
+    constexpr int kLnSliceRows = 32, kLnSlicesPerBlock = GBM / kLnSliceRows, kLnQueue = 8;
+    volatile int* ln_q = ln_flag + 1;          // [kLnQueue]
+    int q_head = 0, q_tail = 0, q_slice = 0;
+    long long ln_cyc = 0, ln_wait_cyc = 0, ln_t0 = clock64();
+    int ln_nslices = 0;
+    auto ln_run_slices = [&](int max_slices) {
+      for (int s_ = 0; s_ < max_slices && q_head != q_tail; ++s_) {
+        const long long t0_ = clock64();
+        if (!(p.debug & 8)) ln_rows(ln_q[q_head & (kLnQueue - 1)], q_slice * kLnSliceRows, (q_slice + 1) * kLnSliceRows);
+        ln_cyc += clock64() - t0_;
+        ++ln_nslices;
+        if (++q_slice == kLnSlicesPerBlock) { q_slice = 0; ++q_head; }
+      }
+    };
+    auto ln_finish_block = [&](int blk, bool wait_all) {
+      if (q_tail - q_head >= kLnQueue - 1) ln_run_slices(kLnSlicesPerBlock);   // never overflows: make room first
+      if (lane == 0) {
+        // this warp's stores of block `blk`: everything except the groups committed since (two per tile)
+        if (wait_all) bulk_wait0();
+        else asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+      }
+      __syncwarp();
+      asm volatile("bar.sync 6, %0;" ::"r"(kEpiGroups * 128) : "memory");
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const int old = atomicAdd(p.ln_counters + blk, 1);
+        const int last = (old == p.num_n_tiles - 1) ? 1 : 0;
+        if (last) {
+          p.ln_counters[blk] = 0;              // ready for the next launch
+          ln_q[q_tail & (kLnQueue - 1)] = blk;
+        }
+        __threadfence();
+        *ln_flag = last;
+      }
+      asm volatile("bar.sync 6, %0;" ::"r"(kEpiGroups * 128) : "memory");
+      if (*ln_flag) ++q_tail;
+    };
     int local = 0;
     for (int tile = cta_first; tile >= 0; tile = next_tile(tile, local, false), ++local) {
       const int rest = tile / p.split_k;
@@ -441,7 +594,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col = n0 + chb * kChunkCols + (gt % kChunkCols);
         if (chb < kNumChunks && col < p.N) bias_v = __ldg(p.bias + col);
       }
+      const long long tw0_ = kLn ? clock64() : 0;
       mbar_wait(&tfull_bar[buf], use & 1, 400 + buf);
+      if (kLn) ln_wait_cyc += clock64() - tw0_;
       tc_fence_after();
       // double-buffered by tile parity: a warp can only be one barrier ahead of the slowest warp of its group, so the
       // slice being overwritten (two tiles old) has no readers left
@@ -504,9 +659,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
               if (pc == hp && row_ok) p.inv_norm[(size_t)m * ((p.N / 3) * 2 / 96) + nb / 96] = inv;
             }
-            unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
+            unsigned char* stg0 = stg_base + (stg_sel & (kSB - 1)) * kStagingBytes;
             stg_sel ^= 1;
-            if (lane == 0) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+            if (lane == 0) { if (kSB == 2) bulk_wait_read1(); else bulk_wait_read0(); }
             __syncwarp();
             tmem_ld_wait();
 #pragma unroll
@@ -608,9 +763,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kPasses = (EPI == SWINB200_EPI_BIAS_GELU) ? 2 : 1;
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass) {
-          unsigned char* stg0 = stg_base + (stg_sel & (kStagingBufs - 1)) * kStagingBytes;
+          unsigned char* stg0 = stg_base + (stg_sel & (kSB - 1)) * kStagingBytes;
           stg_sel ^= 1;
-          if (lane == 0 && !(p.debug & 1)) { if (kStagingBufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+          if (lane == 0 && !(p.debug & 1)) { if (kSB == 2) bulk_wait_read1(); else bulk_wait_read0(); }
           __syncwarp();
           uint4 pk[4];
           if (kF32Out) {
@@ -650,6 +805,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
+      if (kLn) {
+        if (ln_prev_blk >= 0) ln_finish_block(ln_prev_blk, false);
+        ln_prev_blk = m0 / GBM;
+        ln_run_slices(p.ln_slices);
+      }
+    }
+    if (kLn) {
+      const long long tl0_ = clock64();
+      if (ln_prev_blk >= 0) ln_finish_block(ln_prev_blk, true);
+      ln_run_slices(1 << 20);
+      if ((p.debug & 32) && threadIdx.x == 0) {      // probe: per-CTA cycle counts into the head of the stats buffer
+        float* o_ = p.ln_stats + (size_t)blockIdx.x * 8;
+        o_[0] = (float)(clock64() - ln_t0); o_[1] = (float)ln_cyc; o_[2] = (float)ln_wait_cyc; o_[3] = (float)ln_nslices;
+        o_[4] = (float)local; o_[5] = (float)(clock64() - tl0_);
+      }
     }
     if (lane == 0) bulk_wait0();   // all global writes of this warp have completed before the CTA exits
   }
@@ -705,7 +875,7 @@ int make_tmap_2d(CUtensorMap* m, bool f32, const void* base, uint64_t inner, uin
 template <int BN, bool A_MN, bool B_MN, int EPI, bool PAIR>
 static int launch_tc_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
                           const GemmTcParams& p, cudaStream_t s) {
-  using Cfg = GemmCfg<BN, PAIR>;
+  using Cfg = GemmCfg<BN, PAIR, EPI == SWINB200_EPI_BIAS_LN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, PAIR>;
   static bool configured = false;
   if (!configured) {
@@ -770,8 +940,17 @@ static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, c
 
 int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
                  const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const GemmLnFuse* ln) {
   const bool qknorm = (epilogue == SWINB200_EPI_BIAS_QKNORM);
+  if (epilogue == SWINB200_EPI_BIAS_LN) {
+    SWB_CHECK_ARG(ln != nullptr && ln->x_in && ln->gamma && ln->beta && ln->x_out && ln->xb_out && ln->stats && ln->counters,
+                  "gemm(tcgen05): BIAS_LN needs the LayerNorm operands");
+    SWB_CHECK_ARG(N == 768 && a_major == 0 && b_major == 0, "gemm(tcgen05): BIAS_LN is instantiated for 768 output channels, forward operand order");
+    SWB_CHECK_ARG(ln->n_counters >= (M + GBM - 1) / GBM, "gemm(tcgen05): BIAS_LN needs one counter per 128-row block (%d < %d)",
+                  ln->n_counters, (M + GBM - 1) / GBM);
+    SWB_CHECK_ARG(((uintptr_t)ln->x_in % 16 == 0) && ((uintptr_t)ln->x_out % 16 == 0) && ((uintptr_t)ln->xb_out % 16 == 0),
+                  "gemm(tcgen05): BIAS_LN operands must be 16-byte aligned");
+  }
   SWB_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm(tcgen05): lda/ldb must be multiples of 8 elements (16 bytes)");
   SWB_CHECK_ARG(N % 8 == 0 && ldd % 8 == 0, "gemm(tcgen05): N and ldd must be multiples of 8");
   SWB_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0), "gemm(tcgen05): operands must be 16-byte aligned");
@@ -790,11 +969,25 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
     p.debug = dbg;
   }
   p.inv_norm = qknorm ? reinterpret_cast<float*>(D2) : nullptr;
+  p.ln_x_in = nullptr; p.ln_gamma = nullptr; p.ln_beta = nullptr; p.ln_sample_scale = nullptr; p.ln_x_out = nullptr;
+  p.ln_xb_out = nullptr; p.ln_stats = nullptr; p.ln_z = nullptr; p.ln_ldz = 0; p.ln_counters = nullptr;
+  p.ln_rows_per_sample = 1; p.ln_eps = 0.f; p.ln_slices = 0;
+  if (epilogue == SWINB200_EPI_BIAS_LN) {
+    p.ln_x_in = ln->x_in; p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_sample_scale = ln->sample_scale;
+    p.ln_x_out = ln->x_out; p.ln_xb_out = reinterpret_cast<__nv_bfloat16*>(ln->xb_out); p.ln_stats = ln->stats;
+    p.ln_z = reinterpret_cast<const __nv_bfloat16*>(D); p.ln_ldz = ldd; p.ln_counters = ln->counters;
+    p.ln_rows_per_sample = ln->rows_per_sample; p.ln_eps = ln->eps;
+    {
+      static int sl = -1;
+      if (sl < 0) { const char* e = getenv("SWINB200_LN_SLICES"); sl = e ? atoi(e) : 4; }
+      p.ln_slices = max(1, sl);
+    }
+  }
   p.atomic_out = (epilogue == SWINB200_EPI_F32 && (accumulate || split_k > 1)) ? 1 : 0;
   {
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("SWINB200_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
-    p.pair = (pair_env && (BN == 256 || BN == 192)) ? 1 : 0;
+    p.pair = ((pair_env || epilogue == SWINB200_EPI_BIAS_LN) && (BN == 256 || BN == 192)) ? 1 : 0;   // BIAS_LN exists as a pair kernel only
   }
   p.num_m_tiles = p.pair ? (M + 2 * GBM - 1) / (2 * GBM) : (M + GBM - 1) / GBM;
   p.num_n_tiles = (N + BN - 1) / BN;
@@ -824,6 +1017,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
     if (p.pair) return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, true>(tmA, tmB, tmD, tmD2, p, stream);
     return launch_tc_impl<192, false, false, SWINB200_EPI_BIAS_QKNORM, false>(tmA, tmB, tmD, tmD2, p, stream);
   }
+  if (epilogue == SWINB200_EPI_BIAS_LN) return launch_tc_impl<256, false, false, SWINB200_EPI_BIAS_LN, true>(tmA, tmB, tmD, tmD2, p, stream);
   if (BN == 256) return dispatch<256>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
   return dispatch<128>(epilogue, a_major, b_major, tmA, tmB, tmD, tmD2, p, stream);
 }

@@ -151,12 +151,11 @@ class SwinBlockFn(torch.autograd.Function):
         # attention branch
         qkv, inv_norm = ops.qkv_projection(mode, xb, wq, qkv_b.detach(), C, heads)              # (T, 3C): q^, k^, v
         o, lse = ops.window_attn_fwd(qkv, scale_c, bias_c, B, H, W, C, heads, Wh, Ww, s0, s1, mode)
-        z1 = ops.gemm(mode, o, 0, wp, 0, EPI_BIAS, bias=proj_b.detach())                         # (T, C)
-        x_mid, xb_mid, st1 = ops.ln_residual_fwd(z1, x2, n1_w.detach(), n1_b.detach(), dp1, None, H * W, mode)
+        # proj + LayerNorm + DropPath + residual: one kernel on the tcgen05 path (LN in the GEMM epilogue)
+        z1, x_mid, xb_mid, st1 = ops.linear_ln_residual(mode, o, wp, proj_b.detach(), x2, n1_w.detach(), n1_b.detach(), dp1, H * W)
         # MLP branch
         g, h = ops.gemm(mode, xb_mid, 0, w1, 0, EPI_BIAS_GELU, bias=fc1_b.detach())             # (T, hidden) x2
-        z2 = ops.gemm(mode, g, 0, w2, 0, EPI_BIAS, bias=fc2_b.detach())
-        x_out, xb_out, st2 = ops.ln_residual_fwd(z2, x_mid, n2_w.detach(), n2_b.detach(), dp2, None, H * W, mode)
+        z2, x_out, xb_out, st2 = ops.linear_ln_residual(mode, g, w2, fc2_b.detach(), x_mid, n2_w.detach(), n2_b.detach(), dp2, H * W)
         ctx.save_for_backward(xb, qkv, inv_norm, lse, o, z1, st1, xb_mid, h, g, z2, st2, scale_c, bias_c, qkv_w, proj_w,
                               fc1_w, fc2_w, n1_w, n2_w, dp1, dp2)
         ctx.meta = (B, H, W, C, geom, mode)

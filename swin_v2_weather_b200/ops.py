@@ -6,6 +6,8 @@ validated (device, dtype, contiguity) before their raw pointers cross the ABI.
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Optional
 
@@ -204,6 +206,43 @@ def ln_residual_fwd(z, x_in, gamma, beta, sample_scale, pos, rows_per_sample: in
               _chk(sample_scale, "sample_scale", torch.float32, True), _chk(pos, "pos", torch.float32, True),
               x_out.data_ptr(), xb.data_ptr(), stats.data_ptr(), rows, C, rows_per_sample, LN_EPS, _stream())
     return x_out, xb, stats
+
+
+_LN_COUNTERS = {}
+
+
+def linear_ln_residual(mode: ComputeMode, a, w, bias, x_in, gamma, beta, sample_scale, rows_per_sample: int,
+                       fuse: Optional[bool] = None):
+    """z = a @ w^T + bias ; x_out = x_in + sample_scale * (LN(z) gamma + beta)  ->  (z, x_out, xb_out, stats).
+
+    Two implementations with identical results (tests/test_kernels_gpu.py::test_linear_ln_residual_fused_epilogue):
+    * the GEMM followed by the stand-alone LayerNorm kernel (default);
+    * `fuse=True` / SWINB200_FUSE_LN=1, tcgen05 / 768 channels: ONE kernel, the LayerNorm + DropPath scale + residual run
+      inside the GEMM epilogue (swinb200_linear_ln_residual).  Measured on the B200 it is not faster -- fc2: 323 us against
+      216 + 105 us, proj: 225 us against 65 + 105 us -- because the LayerNorm's 600 MB of HBM traffic raises the latency of
+      the operand loads beyond what the 4-stage ring covers, so the model keeps the two kernels."""
+    M, K = a.shape
+    N = w.shape[0]
+    if fuse is None:
+        fuse = os.environ.get("SWINB200_FUSE_LN", "0") == "1"
+    if not (fuse and mode.gemm_backend == BACKEND_TCGEN05 and N == 768):
+        z = gemm(mode, a, 0, w, 0, EPI_BIAS, bias=bias)
+        return (z,) + ln_residual_fwd(z, x_in, gamma, beta, sample_scale, None, rows_per_sample, mode)
+    dev = a.device
+    counters = _LN_COUNTERS.get(dev)
+    n_blocks = (M + 127) // 128
+    if counters is None or counters.numel() < n_blocks:
+        counters = _LN_COUNTERS[dev] = torch.zeros((max(4096, n_blocks),), dtype=torch.int32, device=dev)
+    z = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    x_out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    xb = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    _lib.call("swinb200_linear_ln_residual", BACKEND_TCGEN05, M, N, K, _chk(a, "a", torch.bfloat16), K, _chk(w, "w", torch.bfloat16), K,
+              _chk(bias, "bias", torch.float32, True), z.data_ptr(), N, _chk(x_in, "x_in", torch.float32),
+              _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32),
+              _chk(sample_scale, "sample_scale", torch.float32, True), x_out.data_ptr(), xb.data_ptr(), stats.data_ptr(),
+              rows_per_sample, LN_EPS, counters.data_ptr(), counters.numel(), _stream())
+    return z, x_out, xb, stats
 
 
 def ln_residual_bwd(dx, z, stats, gamma, sample_scale, rows_per_sample: int, mode: ComputeMode, want_dbias_prev=True,

@@ -111,6 +111,33 @@ def test_ln_residual_bwd_ring_kernel():
         assert rel(dbp, zf.grad.sum(0)) < 1e-4      # sum of bf16-rounded dz vs fp32 reference rows
 
 
+@pytest.mark.parametrize("M,K,B", [(300, 768, 1), (2 * 1296, 3072, 2), (64800, 768, 1), (64800, 3072, 1)])
+def test_linear_ln_residual_fused_epilogue(M, K, B):
+    """LayerNorm + DropPath scale + residual inside the proj / fc2 GEMM epilogue (north_star (2), reference
+    swinv2_global.py:490,494) against the two-kernel path and against torch; ragged row blocks, reused counters."""
+    C = 768
+    rps = M // B
+    a = (0.5 * gen(M, K, seed=40)).to(torch.bfloat16)
+    w = (gen(C, K, seed=41) / K ** 0.5).to(torch.bfloat16)
+    bias = 0.1 * gen(C, seed=42)
+    x_in = gen(M, C, seed=43)
+    gamma, beta = 1 + 0.1 * gen(C, seed=44), 0.1 * gen(C, seed=45)
+    for ss in (None, torch.tensor([1.0 / 0.9, 0.0][:B], device=DEV)):
+        for _ in range(2):        # second call: the block counters must have been left at zero
+            z, x_out, xb, stats = ops.linear_ln_residual(ops.MODE_BF16, a, w, bias, x_in, gamma, beta, ss, rps, fuse=True)
+        z_ref = ops.gemm(ops.MODE_BF16, a, 0, w, 0, EPI_BIAS, bias=bias)
+        x_ref, xb_ref, st_ref = ops.ln_residual_fwd(z_ref, x_in, gamma, beta, ss, None, rps, ops.MODE_BF16)
+        assert torch.equal(z, z_ref)
+        assert rel(x_out, x_ref) < 1e-6 and float((x_out - x_ref).abs().max()) < 1e-4
+        assert torch.equal(xb.float(), x_out.to(torch.bfloat16).float())
+        assert rel(stats, st_ref) < 1e-6
+        u = torch.nn.functional.layer_norm(z.float(), (C,), gamma, beta, 1e-5)
+        if ss is not None:
+            u = u * ss.repeat_interleave(rps).view(-1, 1)
+        assert rel(x_out, x_in + u) < 1e-6
+        assert int(ops._LN_COUNTERS[a.device].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C", [96, 192, 768])
 def test_ln_residual_fwd_bwd(dtype, C):
