@@ -533,8 +533,10 @@ attn_tc_fwd2_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 }
 
 int attn_set_phase_buffer3(long long* buf);
+int attn_set_phase_buffer_f3(long long* buf);
 int attn_set_phase_buffer(long long* buf) {
   SWB_CUDA(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
+  if (int e = attn_set_phase_buffer_f3(buf)) return e;
   return attn_set_phase_buffer3(buf);
 }
 

@@ -45,6 +45,8 @@ __device__ __forceinline__ void named_bar_f3(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ long long* g_phase_buf_f3 = nullptr;     // bring-up: per-CTA cycles per phase (tools/attn_phases.py)
+
 template <int D>
 __global__ void __launch_bounds__(kF3Threads, 1)
 attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv,
@@ -61,8 +63,9 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
   uint64_t* sbar = bars + 2;        // S of both query tiles is in tensor memory
   uint64_t* pbar = bars + 3;        // P written back by every compute warp                     (8 warps)
   uint64_t* obar = bars + 4;        // O of both tiles is complete
-  uint64_t* ebar = bars + 5;        // O drained, output rows stored, stage released            (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* ebar = bars + 5;        // output rows stored, stage released                       (8 warps)
+  uint64_t* tbar = bars + 6;        // O is in registers: tensor memory may take the next item's S (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = g.L, LP = g.LP, C = g.C, C3 = 3 * g.C;
@@ -105,6 +108,7 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
     mbar_init(pbar, kF3Compute / 32);
     mbar_init(obar, 1);
     mbar_init(ebar, kF3Compute / 32);
+    mbar_init(tbar, kF3Compute / 32);
     fence_barrier_init();
   }
   if (warp == kF3CtrlWarp) tmem_alloc(tmem_slot, 512);
@@ -160,15 +164,13 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
     if (first < nitems && item_is_box(first)) tma_item(first, 0);
     if (first + stride < nitems && item_is_box(first + stride)) tma_item(first + stride, 1);
     const int nk = LP / 16;
-    uint32_t ph_p = 0, ph_e = 0;
+    uint32_t ph_p = 0, ph_e = 0, ph_t = 0;
     int it = 0;
     for (int item = first; item < nitems; item += stride, ++it) {
       const int s = it & 1;
-      if (it > 0) {
-        mbar_wait(ebar, ph_e, 900); ph_e ^= 1;           // previous item: O drained (TMEM free) and its stage released
-        const int item_next = item + stride;
-        if (item_next < nitems && item_is_box(item_next)) tma_item(item_next, s ^ 1);
-      }
+      // previous item: its O sits in registers -> S of this item may overwrite tensor memory while those rows are still
+      // being parked and stored
+      if (it > 0) { mbar_wait(tbar, ph_t, 903); ph_t ^= 1; }
       mbar_wait(&full[s], (uint32_t)((it >> 1) & 1), 901);
       tc_fence_after();
       const uint32_t q0 = smem_u32(op_ptr(s, 0)), k0 = smem_u32(op_ptr(s, 1)), v0 = smem_u32(op_ptr(s, 2));
@@ -180,6 +182,11 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
         umma_commit(sbar);
       }
       __syncwarp();
+      if (it > 0) {
+        mbar_wait(ebar, ph_e, 900); ph_e ^= 1;           // previous item: output rows stored, its stage released
+        const int item_next = item + stride;
+        if (item_next < nitems && item_is_box(item_next)) tma_item(item_next, s ^ 1);
+      }
       mbar_wait(pbar, ph_p, 902); ph_p ^= 1;
       tc_fence_after();
       if (elect_one_f3()) {
@@ -204,6 +211,10 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
     const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)t * kF3TileCols;
     uint32_t ph_s = 0, ph_o = 0;
     int it = 0;
+    long long* const prof = g_phase_buf_f3;
+    long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t = clock64();
+#define F3_ACC(i) do { if (prof != nullptr && tid == 0) { const long long now_ = clock64(); ph_acc[i] += now_ - ph_t; ph_t = now_; } } while (0)
     for (int item = first; item < nitems; item += stride, ++it) {
       const int s = it & 1;
       int* tok = tokbuf0 + s * kMaxLP;
@@ -222,7 +233,9 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       }
       const bool plain = (bias == nullptr) && !(label_split > 0 && label_split < L);
       const float scale_l2 = scale_p[head] * kLog2e;
+      F3_ACC(6);
       mbar_wait(sbar, ph_s, 910); ph_s ^= 1;
+      F3_ACC(0);
       tc_fence_after();
       float row_sum = 0.f, row_max = -INFINITY, cos_sum = 0.f;      // cos_sum = sum_j p_j cos_j
       if (warp_rows) {
@@ -320,9 +333,11 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pbar);
+      F3_ACC(1);
 
       // ---- O / rowsum -> bf16 rows parked in the (dead) Q^ buffer -> whole-row stores ------------------------------------
       mbar_wait(obar, ph_o, 911); ph_o ^= 1;
+      F3_ACC(2);
       tc_fence_after();
       unsigned char* stage_rows = op_ptr(s, 0);
       if (warp_rows) {
@@ -336,16 +351,25 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
 #pragma unroll
           for (int j = 0; j < 32; ++j) ov[c0 + j] = as_f(v[j]) * inv;
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tbar);
         if (row_ok) park_row<D>(stage_rows, n, ov);
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tbar);
       }
-      tc_fence_before();
+      F3_ACC(3);
       named_bar_f3(1, kF3Compute);
+      F3_ACC(4);
       scatter_rows<D>(stage_rows, L, tok, 0, o, C, head * D, tid, kF3Compute);
       // the stage is released by the barrier below; its next user is the item after next: token table and, for a window
       // that wraps around the shift, the operand gather (TMA boxes are issued by the control warp after the same barrier)
       const int item_nn = item + 2 * stride;
       const bool nn_gather = item_nn < nitems && !item_is_box(item_nn);
       named_bar_f3(2, kF3Compute);                    // every thread has finished reading the parked rows / this tok table
+      F3_ACC(5);
       if (item_nn < nitems) fill_tok(item_nn, tok);
       if (nn_gather) {
         named_bar_f3(3, kF3Compute);
@@ -360,6 +384,9 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       }
       if (lane == 0) mbar_arrive(ebar);
     }
+    if (prof != nullptr && tid == 0 && blockIdx.x < 4096)
+      for (int i = 0; i < 8; ++i) prof[blockIdx.x * 16 + i] = ph_acc[i];
+#undef F3_ACC
   }
   tc_fence_before();
   __syncthreads();
@@ -368,6 +395,11 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+int attn_set_phase_buffer_f3(long long* buf) {
+  SWB_CUDA(cudaMemcpyToSymbol(g_phase_buf_f3, &buf, sizeof(buf)));
+  return SWINB200_OK;
 }
 
 int attn_tcgen05_fwd3(const void* qkv, const float* scale, const float* bias, void* o, float* lse, const AttnGeom& g, cudaStream_t stream) {

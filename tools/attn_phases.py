@@ -15,6 +15,7 @@ buf = torch.zeros(4096 * 16, dtype=torch.int64, device="cuda")
 for shift in ((0, 0), (4, 9)):
     for name in ("fwd", "bwd"):
         _lib.call("swinb200_debug_attn_phase_buffer", buf.data_ptr())
+        buf.zero_()
         o, lse = ops.window_attn_fwd(qkv, scale, None, B, H, W, C, heads, 9, 18, shift[0], shift[1], ops.MODE_BF16, backend=BACKEND_TCGEN05)
         if name == "bwd":
             buf.zero_()
@@ -22,11 +23,10 @@ for shift in ((0, 0), (4, 9)):
             ops.window_attn_bwd(qkv, inv, scale, None, o, d_o, lse, B, H, W, C, heads, 9, 18, shift[0], shift[1], ops.MODE_BF16, backend=BACKEND_TCGEN05)
         torch.cuda.synchronize()
         _lib.call("swinb200_debug_attn_phase_buffer", 0)
-        if name == "fwd":
-            st = buf.view(4096, 16)[:3200].double()
-            n = 7
-            d = (st[:, 1:n] - st[:, 0:n - 1])
-            print(name, shift, "mean cycles per phase:", [int(v) for v in d.mean(0).tolist()], "total", int((st[:, n - 1] - st[:, 0]).mean()))
+        if name == "fwd":   # persistent kernel: [wait S, softmax, wait PV, O read, park+barrier, scatter+barrier, token table / release]
+            st = buf.view(4096, 16)[:148, :8].double()
+            items = 3200 / 148
+            print(name, shift, "mean cycles per phase per item:", [int(v / items) for v in st.mean(0).tolist()], "total/item", int(st.sum(1).mean() / items))
         else:   # persistent kernel: per-CTA accumulated cycles per phase over all its items
             st = buf.view(4096, 16)[:148, :16].double()
             items = 3200 / 148
