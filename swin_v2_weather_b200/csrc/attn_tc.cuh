@@ -96,6 +96,12 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
 }
 
 
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // Row tiles leave the kernel through shared memory: each thread parks its [1 x D] bf16 row (pitch kRowPitch keeps the
 // 16-byte stores conflict-free), then the CTA writes token rows with consecutive threads on consecutive 16-byte pieces,
 // so every global store instruction covers whole 192-byte rows instead of 32 scattered 16-byte fragments.

@@ -266,11 +266,10 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
           }
           row_max = mx * scale_l2;
           const float neg_m = -row_max;
-          // pass 2: p = 2^(scale*cos - max) -> packed bf16 over the columns already consumed; fp32 row sum
-          for (int c0 = 0; c0 < LP; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x16(t_s + c0, v);
-            tmem_ld_wait();
+          // pass 2: p = 2^(scale*cos - max) -> packed bf16 over the columns already consumed; fp32 row sum.  The next 16
+          // columns are requested before the current ones are processed (the stores go to columns [8k, 8k+8), the load in
+          // flight reads [16k+16, 16k+32): never the same)
+          auto softmax16 = [&](const uint32_t (&v)[16], int c0) {
             float p[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(as_f(v[j]), scale_l2, neg_m));
@@ -284,6 +283,19 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
               cos_sum = fmaf(p[j], as_f(v[j]), cos_sum);
             }
             tmem_st_32x8(t_s + c0 / 2, pack8(p, 0), pack8(p, 8));
+          };
+          uint32_t va[16], vb[16];
+          tmem_ld_32x16(t_s, va);
+          for (int c0 = 0; c0 < LP; c0 += 32) {
+            tmem_ld_wait();
+            const bool has_b = c0 + 16 < LP;
+            if (has_b) tmem_ld_32x16(t_s + c0 + 16, vb);
+            softmax16(va, c0);
+            if (has_b) {
+              tmem_ld_wait();
+              if (c0 + 32 < LP) tmem_ld_32x16(t_s + c0 + 32, va);
+              softmax16(vb, c0 + 16);
+            }
           }
         } else {
           // continuous position bias and / or the shifted-window mask (-100 across region labels)
@@ -363,6 +375,9 @@ attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloa
       F3_ACC(3);
       named_bar_f3(1, kF3Compute);
       F3_ACC(4);
+      // per-thread 16-byte pieces of whole 192-byte rows.  (Three TMA box stores per item -- the inverse of the operand loads --
+      // were measured slower: the stage cannot be released before the copy engine has read the parked tile, 2.9 k cycles
+      // per item against 1.8 k for this loop.)
       scatter_rows<D>(stage_rows, L, tok, 0, o, C, head * D, tid, kF3Compute);
       // the stage is released by the barrier below; its next user is the item after next: token table and, for a window
       // that wraps around the shift, the operand gather (TMA boxes are issued by the control warp after the same barrier)

@@ -58,6 +58,35 @@ def test_new_entry_points_reject_bad_arguments():
     assert b"sources" in lib.swinb200_last_error()
 
 
+def test_linear_ln_residual_rejects_what_it_is_not_built_for():
+    """The fused GEMM + LayerNorm entry point: null operands are argument errors; other widths / back ends are refused with
+    a message that names the two-kernel path (no silent fallback inside the library)."""
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    rc = lib.swinb200_linear_ln_residual(1, 256, 768, 768, None, 768, p16, 768, None, p16, 768, p16, p16, p16, None, p16, p16, p16,
+                                         256, 1e-5, p16, 2, None)
+    assert rc == 1 and b"null pointer" in lib.swinb200_last_error()
+    rc = lib.swinb200_linear_ln_residual(1, 256, 512, 768, p16, 768, p16, 768, None, p16, 512, p16, p16, p16, None, p16, p16, p16,
+                                         256, 1e-5, p16, 2, None)
+    assert rc == 3 and b"768 output channels" in lib.swinb200_last_error()
+    rc = lib.swinb200_linear_ln_residual(0, 256, 768, 768, p16, 768, p16, 768, None, p16, 768, p16, p16, p16, None, p16, p16, p16,
+                                         256, 1e-5, p16, 2, None)
+    assert rc == 3 and b"swinb200_ln_residual_fwd" in lib.swinb200_last_error()
+    rc = lib.swinb200_linear_ln_residual(1, 1024, 768, 768, p16, 768, p16, 768, None, p16, 768, p16, p16, p16, None, p16, p16, p16,
+                                         256, 1e-5, p16, 2, None)        # 8 row blocks, 2 counters
+    assert rc == 1 and b"one counter per 128-row block" in lib.swinb200_last_error()
+
+
+def test_attention_back_end_is_chosen_from_the_shape():
+    from swin_v2_weather_b200 import ops
+    from swin_v2_weather_b200._lib import BACKEND_SIMT, BACKEND_TCGEN05
+    for heads in (4, 6, 8, 12, 16):      # head_dim 192, 128, 96, 64, 48 at C = 768: tensor cores, any window
+        for window in ((9, 18), (6, 12), (12, 24), (18, 36)):
+            assert ops.attn_backend_for(ops.MODE_BF16, 768, heads, *window) == BACKEND_TCGEN05
+    assert ops.attn_backend_for(ops.MODE_BF16, 160, 2, 9, 18) == BACKEND_SIMT          # head_dim 80: CUDA cores
+    assert ops.attn_backend_for(ops.MODE_FP32, 768, 8, 9, 18) == BACKEND_SIMT          # fp32 validation mode
+
+
 def test_argument_errors_come_back_as_codes_not_crashes():
     lib = _lib.load()
     # null pointers / bad shapes are rejected before any CUDA call
