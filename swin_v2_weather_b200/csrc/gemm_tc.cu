@@ -694,16 +694,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]); }
         continue;
       }
+      // The operand is fetched with lane l on the 16-byte piece (l & 3) of rows (l >> 2) + 8 i: one load instruction covers
+      // 8 rows x 64 contiguous bytes.  (Lane = row, four pieces each, is 32 different rows per instruction = 32 L1 tag
+      // cycles, 4096 per tile for the 16 warps against 6144 cycles of tensor time.)  The pieces reach the thread that owns
+      // their row through the staging buffer this chunk's output will use next.
       uint4 aux_nxt[4];
       auto aux_fetch = [&](int chn) {
         if (kHasAux) {
           const int nbn = n0 + chn * kChunkCols;
-          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.aux) +
-                                     ((size_t)m * p.ld_aux + nbn) * (kF32Out ? 4 : 2);
+          const int piece = lane & 3;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            aux_nxt[q] = (row_ok && chn < kNumChunks && nbn + q * (kChunkCols / 4) < p.N)
-                             ? __ldg(reinterpret_cast<const uint4*>(src) + q) : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 4; ++i) {
+            const int mr = m0 + mrow0 + i * 8 + (lane >> 2);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.aux) + ((size_t)mr * p.ld_aux + nbn) * (kF32Out ? 4 : 2);
+            aux_nxt[i] = (mr < p.M && chn < kNumChunks && nbn + piece * (kChunkCols / 4) < p.N)
+                             ? __ldg(reinterpret_cast<const uint4*>(src) + piece) : make_uint4(0, 0, 0, 0);
+          }
         }
       };
       aux_fetch(grp);
@@ -713,8 +719,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (nb >= p.N) break;                       // whole chunk beyond N (uniform across the group)
         uint4 aux_cur[4];
         if (kHasAux) {
+          unsigned char* xb = stg_base + (stg_sel & (kSB - 1)) * kStagingBytes;
+          if (lane == 0 && !(p.debug & 1)) { if (kSB == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+          __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) aux_cur[q] = aux_nxt[q];
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(staging_chunk(xb, i * 8 + (lane >> 2), lane & 3)) = aux_nxt[i];
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) aux_cur[q] = *reinterpret_cast<const uint4*>(staging_chunk(xb, lane, q));
+          __syncwarp();                             // everyone has its row before the output pieces overwrite the buffer
           aux_fetch(ch + kEpiGroups);
         }
         float v[kChunkCols];
