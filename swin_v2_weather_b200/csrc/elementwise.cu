@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(256) ln_residual_fwd_kernel(const T* __restric
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * warps_per_block;
   const float invC = 1.0f / (float)C;
-  for (int row = warp_global; row < rows; row += nwarps) {
+  // rows are visited from the END of the tensor: the GEMM that produced z wrote its last rows last, so they are still in L2
+  for (int ri = warp_global; ri < rows; ri += nwarps) {
+    const int row = rows - 1 - ri;
     float v[NCHUNK][8], xi[NCHUNK][8];
     float sum = 0.f;
     // every global load of the row (branch output and residual stream) is issued before the first reduction
@@ -520,21 +522,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (c < cols) {
-    // four independent 16-byte loads in flight per thread: the pass is pure HBM streaming
+    // four independent 16-byte loads in flight per thread: the pass is pure HBM streaming.  Rows are visited from the END of
+    // the tensor: the kernel that produced x wrote its last rows last, so that part is still in L2.
     const int step = gridDim.y * 8;
+    const T* xe = x + (size_t)(rows - 1) * ld + c;
     int r = blockIdx.y * 8 + ty;
     for (; r + 3 * step < rows; r += 4 * step) {
       float v0[8], v1[8], v2[8], v3[8];
-      ld8(x + (size_t)r * ld + c, v0);
-      ld8(x + (size_t)(r + step) * ld + c, v1);
-      ld8(x + (size_t)(r + 2 * step) * ld + c, v2);
-      ld8(x + (size_t)(r + 3 * step) * ld + c, v3);
+      ld8(xe - (size_t)r * ld, v0);
+      ld8(xe - (size_t)(r + step) * ld, v1);
+      ld8(xe - (size_t)(r + 2 * step) * ld, v2);
+      ld8(xe - (size_t)(r + 3 * step) * ld, v3);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
     }
     for (; r < rows; r += step) {
       float v[8];
-      ld8(x + (size_t)r * ld + c, v);
+      ld8(xe - (size_t)r * ld, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += v[e];
     }
@@ -936,7 +940,8 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
     // ------------------------------------------------ producer ------------------------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+        const int tile = ntiles - 1 - ti;          // from the end: the tail of dx (just written by the dgrad GEMM) is still in L2
         const int stage = it % kLnbStages;
         if (it >= kLnbStages) lnb_mbar_wait(&empty[stage], (uint32_t)((it / kLnbStages - 1) & 1));
         const int r0 = tile * kLnbRows;
@@ -958,7 +963,8 @@ ln_bwd_rowwarp_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restr
     unsigned char* obuf = lsm + SM::kOffOut + warp * 2 * C * 2;
     const float invC = 1.0f / (float)C;
     int it = 0, nstores = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+      const int tile = ntiles - 1 - ti;
       const int stage = it % kLnbStages;
       const int row = tile * kLnbRows + warp;
       const bool active = row < rows;
