@@ -6,6 +6,8 @@ activation storage + fp32 row statistics -- ~24.6 KB/token, 1.6 GB per block per
 """
 from __future__ import annotations
 
+import os
+
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -193,21 +195,31 @@ class SwinBlockFn(torch.autograd.Function):
 
         # ---- MLP branch: x_out = x_mid + dp2 * LN2(fc2(gelu(fc1(xb_mid))))
         dz2, dg2, db2, dbias_fc2 = ops.ln_residual_bwd(dx_out, z2, st2, n2_w.detach(), dp2, H * W, mode, acc=acc["ln2"].view(3, C))
+        # Order: every tensor is consumed right after it was produced, and consecutive kernels alternate their direction over
+        # the token rows (GEMMs ascend, the row-wise kernels descend), so each one starts on the ~100 MB its predecessor left
+        # in L2.  The two weight gradients that do not touch the fresh tensor (fc2: dz2, g; proj: dz1, o) run last.
+        reorder = os.environ.get("SWINB200_BWD_ORDER", "1") != "0"
         dh = ops.gemm(mode, dz2, 0, w2, 1, EPI_DGELU, aux=h)                                     # (T, hidden)
         dbias_fc1 = ops.colsum(dh, out=acc["b_fc1"])          # right behind the GEMM that wrote dh: its tail is still in L2
-        dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
+        if not reorder:
+            dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
         dx_mid = ops.gemm(mode, dh, 0, w1, 1, EPI_ADD_F32, aux=dx_out)                           # fp32 (T, C)
         dw_fc1 = wgrad(dh, xb_mid, hid, C, "w_fc1")
         del dh
+        if reorder:
+            dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
         # ---- attention branch: x_mid = x + dp1 * LN1(proj(attn(qkv(xb))))
         dz1, dg1, db1, dbias_proj = ops.ln_residual_bwd(dx_mid, z1, st1, n1_w.detach(), dp1, H * W, mode, acc=acc["ln1"].view(3, C))
         d_o = ops.gemm(mode, dz1, 0, wp, 1, EPI_BIAS)                                            # (T, C)
-        dw_proj = wgrad(dz1, o, C, C, "w_proj")
+        if not reorder:
+            dw_proj = wgrad(dz1, o, C, C, "w_proj")
         dqkv, dscale, dbias_tab = ops.window_attn_bwd(qkv, inv_norm, scale_c, bias_c, o, d_o, lse, B, H, W, C, heads, Wh, Ww,
                                                        s0, s1, mode, dscale=acc["dscale"])
         dbias_qkv = ops.colsum(dqkv, out=acc["b_qkv"])
         dx_in = ops.gemm(mode, dqkv, 0, wq, 1, EPI_ADD_F32, aux=dx_mid)                          # fp32 (T, C)
         dw_qkv = wgrad(dqkv, xb, 3 * C, C, "w_qkv")
+        if reorder:
+            dw_proj = wgrad(dz1, o, C, C, "w_proj")
         return (dx_in.view(B, H, W, C), None, dscale, dbias_tab, dw_qkv, dbias_qkv, dw_proj, dbias_proj, dg1, db1, dw_fc1,
                 dbias_fc1, dw_fc2, dbias_fc2, dg2, db2, None, None, None, None)
 
