@@ -99,7 +99,8 @@ class KernelTimer:
               "swinb200_ln_residual_fwd": "ln_fwd", "swinb200_ln_residual_bwd": "ln_bwd", "swinb200_colsum": "colsum",
               "swinb200_patchify": "patchify", "swinb200_unpatchify": "unpatchify", "swinb200_latw_l2_fwd": "loss",
               "swinb200_latw_l2_bwd": "loss", "swinb200_transpose_f32": "transpose", "swinb200_pos_embed_grad": "transpose",
-              "swinb200_cast_f32_to_bf16": "cast", "swinb200_linear_ln_residual": "gemm_ln"}
+              "swinb200_cast_f32_to_bf16": "cast", "swinb200_linear_ln_residual": "gemm_ln",
+              "swinb200_linear_wgrad": "gemm_wgrad"}
 
     def __init__(self):
         self.records = []   # (family, flops, bytes, start_event, end_event)
@@ -128,6 +129,13 @@ class KernelTimer:
             flops = 2.0 * M * N * K
             bytes_ = 2.0 * (M * K + N * K) + 12.0 * M * N
             variant = f"M{M}_N{N}_K{K}_a0b0_bias_ln_residual"
+        if fam == "gemm_wgrad":
+            # weight + bias gradient in one kernel: dW (n_out, n_in) += dY^T X, dbias += column sums of dY (read from the staged tiles)
+            M, N, K = args[1], args[2], args[3]
+            fam = "gemm_tcgen05"
+            flops = 2.0 * M * N * K
+            bytes_ = 2.0 * (M * K + N * K) + 4.0 * M * N
+            variant = f"M{M}_N{N}_K{K}_a1b1_f32_colsum" + (f"_splitk{args[11]}" if args[11] > 1 else "")
         if fam == "gemm":
             backend, M, N, K = args[0], args[1], args[2], args[3]
             fam = "gemm_tcgen05" if backend == 1 else "gemm_simt"

@@ -99,6 +99,16 @@ int swinb200_gemm(int backend, int M, int N, int K, const void* A, int a_major, 
                   void* D2, const void* aux, int ld_aux, int out_dtype, int accumulate, int split_k,
                   void* stream);
 
+/* ---- weight + bias gradient of nn.Linear in one kernel ----------------------------------------------------
+ * dW[n_out, n_in] += dY^T X  (split-K, fp32 TMA reduce-add into a pre-initialised dW) ;  dbias[n_out] += column sums of dY
+ *   == autograd of `self.qkv` / `self.mlp.fc1` w.r.t. weight and bias (swinv2_global.py:181/300, timm Mlp.fc1): the bias
+ *   gradient is the sum over tokens of the dY tiles the weight-gradient GEMM stages in shared memory anyway, taken there
+ *   by the epilogue warps while the main loop runs -- dY is not read again by a column-sum pass.  dY (T, n_out) and
+ *   X (T, n_in) bf16 token-major; dbias may be NULL.  tcgen05 back end, n_out a multiple of 256, n_in >= 256; otherwise
+ *   SWINB200_ERR_UNSUPPORTED (the caller runs swinb200_gemm + swinb200_colsum). */
+int swinb200_linear_wgrad(int backend, int n_out, int n_in, int T, const void* dY, int ldy, const void* X, int ldx,
+                          float* dW, int lddw, float* dbias, int split_k, void* stream);
+
 /* ---- Linear + LayerNorm + DropPath + residual in one kernel -----------------------------------------
  * z = A W^T + bias (stored, bf16: the backward needs it) ; u = LN_N(z) * gamma + beta (* sample_scale[row /
  * rows_per_sample] if given) ; x_out = x_in + u ; xb_out = bf16(x_out) ; stats[row] = (mean, rstd)

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "swinb200_latw_l1_bwd": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
     "swinb200_latw_acc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "swinb200_gemm": [_I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "swinb200_linear_wgrad": [_I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P],
     "swinb200_linear_ln_residual": [_I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, c_float, _P, _I, _P],
     "swinb200_ln_residual_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, c_float, _P],
     "swinb200_ln_residual_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],

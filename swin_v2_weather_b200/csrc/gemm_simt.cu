@@ -114,7 +114,7 @@ static int launch_simt(int M, int N, int K, const T* A, int a_major, int lda, co
 
 int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
                  const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
-                 cudaStream_t stream, const GemmLnFuse* ln = nullptr);
+                 cudaStream_t stream, const GemmLnFuse* ln = nullptr, float* colsum_out = nullptr);
 
 }  // namespace swinb200
 
@@ -153,6 +153,21 @@ extern "C" int swinb200_gemm(int backend, int M, int N, int K, const void* A, in
   if (in_dtype == SWINB200_F32)
     return launch_simt<float>(M, N, K, (const float*)A, a_major, lda, (const float*)B, b_major, ldb, epilogue, bias, D, ldd, D2, aux, ld_aux, accumulate, s);
   SWB_CHECK_ARG(false, "gemm: bad in_dtype %d", in_dtype);
+}
+
+extern "C" int swinb200_linear_wgrad(int backend, int n_out, int n_in, int T, const void* dY, int ldy, const void* X, int ldx,
+                                     float* dW, int lddw, float* dbias, int split_k, void* stream) {
+  SWB_CHECK_ARG(n_out > 0 && n_in > 0 && T > 0, "linear_wgrad: bad shape n_out=%d n_in=%d T=%d", n_out, n_in, T);
+  SWB_CHECK_ARG(dY && X && dW, "linear_wgrad: null pointer");
+  SWB_CHECK_ARG(ldy >= n_out && ldx >= n_in && lddw >= n_in && split_k >= 1, "linear_wgrad: leading dimension too small");
+  if (backend != SWINB200_GEMM_TCGEN05 || n_out % 256 != 0 || n_in < 256) {
+    set_error("linear_wgrad: the fused weight + bias gradient is a tcgen05 / bf16 kernel for n_out a multiple of 256 and "
+              "n_in >= 256; run swinb200_gemm(a1, b1, EPI_F32, accumulate) + swinb200_colsum for backend %d, n_out = %d, n_in = %d",
+              backend, n_out, n_in);
+    return SWINB200_ERR_UNSUPPORTED;
+  }
+  return gemm_tcgen05(n_out, n_in, T, dY, 1, ldy, X, 1, ldx, SWINB200_EPI_F32, nullptr, dW, lddw, nullptr, nullptr, 0, 1, split_k,
+                      (cudaStream_t)stream, nullptr, dbias);
 }
 
 extern "C" int swinb200_linear_ln_residual(int backend, int M, int N, int K, const void* A, int lda, const void* W, int ldw,

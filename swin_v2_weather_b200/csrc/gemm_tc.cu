@@ -59,6 +59,7 @@ struct GemmTcParams {
   int ln_rows_per_sample;
   float ln_eps;
   int ln_slices;                  // 32-row LayerNorm slices a CTA may run per tile boundary
+  float* colsum_out;              // weight-gradient GEMMs (A m-major): column sums of A (= bias gradient) += here, or null
 };
 
 // PAIR: two CTAs of a cluster (two SMs) share one 256 x BN tile: tcgen05.mma.cta_group::2 reads the A rows and one half
@@ -279,6 +280,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* sfull = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars + 192);          // [kSched] response has landed
   uint64_t* sempty = sfull + kSched;                                                  // [kSched] every role has read it (leader's copy)
 
+  // Weight gradients (A = dY read m-major): the bias gradient is the column sum of dY, i.e. the sum over k of the very A tiles
+  // this kernel stages.  The epilogue warps, idle during the main loop, add up every stage after its MMAs have completed and
+  // before the producer refills it (tiles of the first column block only), so dY is not read a third time from HBM by a
+  // separate column-sum kernel.  cs_bar[stage]: the 16 epilogue warps are done with the stage.
+  constexpr bool kCanCs = A_MN && B_MN && PAIR && (EPI == SWINB200_EPI_F32) && (BN == 256);
+  const bool cs_on = kCanCs && p.colsum_out != nullptr;
+  uint64_t* cs_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBias);     // the bias table is unused by this epilogue
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == kProducerWarp && lane == 0) {
@@ -293,6 +302,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], (PAIR ? 2 : 1) * 4 * kEpiGroups);   // PAIR: both CTAs' epilogue warps report to the leader
+    }
+    if (kCanCs) {
+      for (int s = 0; s < Cfg::kStages; ++s) mbar_init(&cs_bar[s], 4 * kEpiGroups);
     }
     if (PAIR) {
       for (int q = 0; q < kSched; ++q) {
@@ -359,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+        if (kCanCs && cs_on) mbar_wait(&cs_bar[stage], phase ^ 1, 110 + stage);
         if (elect_one()) {
           unsigned char* sa = smem + stage * Cfg::kStage;
           unsigned char* sb = sa + Cfg::kStageA;
@@ -453,6 +466,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_bias = kBiasEpi && p.bias != nullptr;
     const int mrow0 = quarter * 32;        // first tile row of this warp
     int qk_tiles = 0;                      // BIAS_QKNORM: tiles that exchanged norms so far
+    int cs_stage = 0;                      // column sums of A: the stage / phase the main loop is at (all tiles, all k blocks)
+    uint32_t cs_phase = 0;
     // ---- BIAS_LN: x_out = x_in + s * (LN(z) gamma + beta) for a 128-row block whose last column tile has just landed ----------
     // Every CTA counts the tiles it has *completely* written (all 16 warps' TMA stores finished) per 128-row block; the CTA
     // that brings a block's count to num_n_tiles re-reads the block's bf16 rows of z (L2-hot, written by up to three SMs)
@@ -586,6 +601,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (rest / p.num_n_tiles) * (PAIR ? 2 * GBM : GBM) + (int)crank * GBM;
       const int buf = local & 1;
       const uint32_t use = (uint32_t)(local >> 1);
+      if (kCanCs && cs_on) {
+        // follow the main loop of this tile: stage `cs_stage` is ours between the completion of its MMAs (empty_bar, which
+        // the commit multicasts to both CTAs of the pair) and the producer's refill (which waits for cs_bar)
+        const int ks_ = tile % p.split_k;
+        const int kb0_ = ks_ * p.kb_per_split, kb1_ = min(p.kb_total, kb0_ + p.kb_per_split);
+        const bool sum_tile = (n0 == 0);
+        // thread <-> (64-column box, 8-row k group, 4-byte word of the 128-byte swizzled row = two columns)
+        const int cs_box = ew >> 3, cs_kg = ew & 7;
+        float cs0 = 0.f, cs1 = 0.f;
+        for (int kb = kb0_; kb < kb1_; ++kb) {
+          mbar_wait(&empty_bar[cs_stage], cs_phase, 120 + cs_stage);
+          if (sum_tile) {
+            const unsigned char* box = smem + cs_stage * Cfg::kStage + cs_box * (64 * GBK * 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = cs_kg * 8 + j;
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((lane >> 2) ^ (k & 7))) << 4) + (lane & 3) * 4);
+              cs0 += __uint_as_float(w2 << 16);
+              cs1 += __uint_as_float(w2 & 0xffff0000u);
+            }
+          }
+          fence_proxy_async_smem();            // these generic-proxy reads are ordered before the async-proxy refill
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs_bar[cs_stage]);
+          if (++cs_stage == Cfg::kStages) { cs_stage = 0; cs_phase ^= 1; }
+        }
+        if (sum_tile) {
+          // fold the 8 k groups of each box through the (idle) staging buffers, then one atomic per column
+          // (every warp parks its partial sums in its OWN staging buffer: only it knows when its stores have drained)
+          constexpr int kWarpStg = kSB * kStagingBytes / 4;                       // floats per warp
+          float* xch = reinterpret_cast<float*>(smem + Cfg::kOffStaging);
+          if (lane == 0) bulk_wait_read0();      // this warp's output pieces of the previous tile have left its staging buffers
+          __syncwarp();
+          xch[ew * kWarpStg + lane * 2] = cs0;
+          xch[ew * kWarpStg + lane * 2 + 1] = cs1;
+          asm volatile("bar.sync 7, %0;" ::"r"(kEpiGroups * 128) : "memory");
+          const int t_ = threadIdx.x;            // 0 .. 511: threads 0..127 own one column each
+          if (t_ < GBM) {
+            const int bx = t_ >> 6, wd = (t_ & 63) >> 1, hf = t_ & 1;
+            float tot = 0.f;
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) tot += xch[(bx * 8 + g8) * kWarpStg + wd * 2 + hf];
+            const int col = m0 + t_;
+            if (col < p.M) atomicAdd(p.colsum_out + col, tot);
+          }
+          asm volatile("bar.sync 7, %0;" ::"r"(kEpiGroups * 128) : "memory");   // before the staging buffers take output pieces
+        }
+      }
       // this group's slice of the bias vector goes through shared memory (there is no L1 left beside the 225 KB of
       // operand stages, so a per-chunk __ldg would expose an L2 round trip): fetched before the accumulator wait
       float bias_v = 0.f;
@@ -953,7 +1016,7 @@ static int dispatch(int epi, int a_major, int b_major, const CUtensorMap& tmA, c
 
 int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const void* B, int b_major, int ldb, int epilogue,
                  const float* bias, void* D, int ldd, void* D2, const void* aux, int ld_aux, int accumulate, int split_k,
-                 cudaStream_t stream, const GemmLnFuse* ln) {
+                 cudaStream_t stream, const GemmLnFuse* ln, float* colsum_out) {
   const bool qknorm = (epilogue == SWINB200_EPI_BIAS_QKNORM);
   if (epilogue == SWINB200_EPI_BIAS_LN) {
     SWB_CHECK_ARG(ln != nullptr && ln->x_in && ln->gamma && ln->beta && ln->x_out && ln->xb_out && ln->stats && ln->counters,
@@ -984,7 +1047,7 @@ int gemm_tcgen05(int M, int N, int K, const void* A, int a_major, int lda, const
   p.inv_norm = qknorm ? reinterpret_cast<float*>(D2) : nullptr;
   p.ln_x_in = nullptr; p.ln_gamma = nullptr; p.ln_beta = nullptr; p.ln_sample_scale = nullptr; p.ln_x_out = nullptr;
   p.ln_xb_out = nullptr; p.ln_stats = nullptr; p.ln_z = nullptr; p.ln_ldz = 0; p.ln_counters = nullptr;
-  p.ln_rows_per_sample = 1; p.ln_eps = 0.f; p.ln_slices = 0;
+  p.ln_rows_per_sample = 1; p.ln_eps = 0.f; p.ln_slices = 0; p.colsum_out = colsum_out;
   if (epilogue == SWINB200_EPI_BIAS_LN) {
     p.ln_x_in = ln->x_in; p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_sample_scale = ln->sample_scale;
     p.ln_x_out = ln->x_out; p.ln_xb_out = reinterpret_cast<__nv_bfloat16*>(ln->xb_out); p.ln_stats = ln->stats;

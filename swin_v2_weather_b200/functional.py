@@ -200,11 +200,11 @@ class SwinBlockFn(torch.autograd.Function):
         # in L2.  The two weight gradients that do not touch the fresh tensor (fc2: dz2, g; proj: dz1, o) run last.
         reorder = os.environ.get("SWINB200_BWD_ORDER", "1") != "0"
         dh = ops.gemm(mode, dz2, 0, w2, 1, EPI_DGELU, aux=h)                                     # (T, hidden)
-        dbias_fc1 = ops.colsum(dh, out=acc["b_fc1"])          # right behind the GEMM that wrote dh: its tail is still in L2
         if not reorder:
             dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
         dx_mid = ops.gemm(mode, dh, 0, w1, 1, EPI_ADD_F32, aux=dx_out)                           # fp32 (T, C)
-        dw_fc1 = wgrad(dh, xb_mid, hid, C, "w_fc1")
+        # weight + bias gradient of fc1 in one kernel (the bias gradient is the column sum of the dh tiles the GEMM stages)
+        dw_fc1, dbias_fc1 = ops.linear_wgrad(mode, dh, xb_mid, acc["w_fc1"].view(hid, C), acc["b_fc1"], ops.wgrad_split_k(hid, C, T))
         del dh
         if reorder:
             dw_fc2 = wgrad(dz2, g, C, hid, "w_fc2")
@@ -215,9 +215,8 @@ class SwinBlockFn(torch.autograd.Function):
             dw_proj = wgrad(dz1, o, C, C, "w_proj")
         dqkv, dscale, dbias_tab = ops.window_attn_bwd(qkv, inv_norm, scale_c, bias_c, o, d_o, lse, B, H, W, C, heads, Wh, Ww,
                                                        s0, s1, mode, dscale=acc["dscale"])
-        dbias_qkv = ops.colsum(dqkv, out=acc["b_qkv"])
         dx_in = ops.gemm(mode, dqkv, 0, wq, 1, EPI_ADD_F32, aux=dx_mid)                          # fp32 (T, C)
-        dw_qkv = wgrad(dqkv, xb, 3 * C, C, "w_qkv")
+        dw_qkv, dbias_qkv = ops.linear_wgrad(mode, dqkv, xb, acc["w_qkv"].view(3 * C, C), acc["b_qkv"], ops.wgrad_split_k(3 * C, C, T))
         if reorder:
             dw_proj = wgrad(dz1, o, C, C, "w_proj")
         return (dx_in.view(B, H, W, C), None, dscale, dbias_tab, dw_qkv, dbias_qkv, dw_proj, dbias_proj, dg1, db1, dw_fc1,

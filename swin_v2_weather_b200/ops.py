@@ -208,6 +208,27 @@ def ln_residual_fwd(z, x_in, gamma, beta, sample_scale, pos, rows_per_sample: in
     return x_out, xb, stats
 
 
+def linear_wgrad(mode: ComputeMode, dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor],
+                 split_k: int, fuse: Optional[bool] = None):
+    """dw (n_out, n_in) fp32 += dy^T x ;  dbias (n_out) fp32 += column sums of dy  (both pre-zeroed accumulators).
+    tcgen05, n_out a multiple of 256: ONE kernel -- the epilogue warps of the weight-gradient GEMM sum the dy tiles the main
+    loop stages in shared memory (swinb200_linear_wgrad), so dy is not read again by a column-sum pass.  Otherwise (and with
+    SWINB200_FUSE_COLSUM=0): the split-K GEMM followed by swinb200_colsum."""
+    T, n_out = dy.shape
+    n_in = x.shape[1]
+    if fuse is None:
+        fuse = os.environ.get("SWINB200_FUSE_COLSUM", "1") != "0"
+    if fuse and dbias is not None and mode.gemm_backend == BACKEND_TCGEN05 and n_out % 256 == 0 and n_in >= 256:
+        _lib.call("swinb200_linear_wgrad", BACKEND_TCGEN05, n_out, n_in, T, _chk(dy, "dy", torch.bfloat16), n_out,
+                  _chk(x, "x", torch.bfloat16), n_in, _chk(dw, "dw", torch.float32), n_in, _chk(dbias, "dbias", torch.float32),
+                  int(split_k), _stream())
+        return dw, dbias
+    gemm(mode, dy, 1, x, 1, EPI_F32, out=dw, accumulate=True, split_k=split_k)
+    if dbias is not None:
+        colsum(dy, out=dbias)
+    return dw, dbias
+
+
 _LN_COUNTERS = {}
 
 

@@ -111,6 +111,25 @@ def test_ln_residual_bwd_ring_kernel():
         assert rel(dbp, zf.grad.sum(0)) < 1e-4      # sum of bf16-rounded dz vs fp32 reference rows
 
 
+@pytest.mark.parametrize("T,n_out,n_in", [(1000, 512, 256), (5000, 768, 768), (64800, 3072, 768), (64800, 2304, 768)])
+def test_linear_wgrad_with_bias_gradient_in_the_same_kernel(T, n_out, n_in):
+    """Weight + bias gradient of nn.Linear (reference: autograd of swinv2_global.py:181/300 and timm Mlp.fc1): the column sums
+    of dY taken inside the weight-gradient GEMM against the GEMM + column-sum kernels and against torch; ragged token
+    counts (last k block partly out of range), accumulation into non-zero buffers."""
+    dy = (0.5 * gen(T, n_out, seed=50)).to(torch.bfloat16)
+    x = (0.5 * gen(T, n_in, seed=51)).to(torch.bfloat16)
+    sk = ops.wgrad_split_k(n_out, n_in, T)
+    dw0, db0 = gen(n_out, n_in, seed=52), gen(n_out, seed=53)
+    dw, db = ops.linear_wgrad(ops.MODE_BF16, dy, x, dw0.clone(), db0.clone(), sk, fuse=True)
+    dw_r, db_r = ops.linear_wgrad(ops.MODE_BF16, dy, x, dw0.clone(), db0.clone(), sk, fuse=False)
+    want_w = dw0.double() + dy.double().t() @ x.double()
+    want_b = db0.double() + dy.double().sum(0)
+    assert rel(dw, want_w.float()) < 5e-5 and rel(dw_r, want_w.float()) < 5e-5      # fp32 accumulation over up to 64,800 tokens
+    assert rel(dw, dw_r) < 1e-5
+    assert rel(db, want_b.float()) < 1e-5 and rel(db_r, want_b.float()) < 1e-5
+    assert float((db.double() - want_b).abs().max()) < 1e-3 * float(want_b.abs().max())
+
+
 @pytest.mark.parametrize("M,K,B", [(300, 768, 1), (2 * 1296, 3072, 2), (64800, 768, 1), (64800, 3072, 1)])
 def test_linear_ln_residual_fused_epilogue(M, K, B):
     """LayerNorm + DropPath scale + residual inside the proj / fc2 GEMM epilogue (north_star (2), reference
