@@ -221,6 +221,7 @@ def make_loss(device, config4=False):
 def run_ours(args):
     from swin_v2_weather_b200 import _lib, distributed as D
     rank, world, local = D.init_from_env()
+    numa_bound = D.bind_to_gpu_numa_node(local) if os.environ.get("SWINB200_NUMA_BIND", "1") != "0" else False
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -476,7 +477,7 @@ def run_ours(args):
                    "attention_backend": "tcgen05" if ops_attn_is_tc(args.mode) else "cuda-core"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss},
+                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss, "numa_bound": bool(numa_bound)},
         "gpu_launches": launches,
         "roofline": roof,
         "kernel_families": families,

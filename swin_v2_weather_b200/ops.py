@@ -245,7 +245,8 @@ def linear_ln_residual(mode: ComputeMode, a, w, bias, x_in, gamma, beta, sample_
     M, K = a.shape
     N = w.shape[0]
     if fuse is None:
-        fuse = os.environ.get("SWINB200_FUSE_LN", "0") == "1"
+        env = os.environ.get("SWINB200_FUSE_LN", "0")          # 1: every eligible GEMM; 2: only the long-K ones (fc2)
+        fuse = env == "1" or (env == "2" and K >= 2048)
     if not (fuse and mode.gemm_backend == BACKEND_TCGEN05 and N == 768):
         z = gemm(mode, a, 0, w, 0, EPI_BIAS, bias=bias)
         return (z,) + ln_residual_fwd(z, x_in, gamma, beta, sample_scale, None, rows_per_sample, mode)
