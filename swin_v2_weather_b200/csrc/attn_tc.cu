@@ -562,11 +562,12 @@ int attn_tcgen05_fwd(const void* qkv, const float* scale, const float* bias, voi
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SWINB200_ATTN_FWD");
-    variant = e ? atoi(e) : 3;   // 1 = first SS-mode kernel; 2 = two CTAs per SM, cp.async gather; 3 = persistent, TMA boxes, double-buffered; 4 = generic
+    variant = e ? atoi(e) : 5;   // 1 = first SS-mode kernel; 2 = two CTAs per SM, cp.async gather; 3 = persistent, TMA boxes, double-buffered; 4 = tiled (attn_tc_gen.cu); 5 = two items in flight per SM (attn_tc_fwd4.cu)
   }
   // with a bias table the tiled kernel is the faster forward on every geometry (434 vs 660 us at 9x18 / 8 heads): its table
   // values are prefetched and reach their rows through a shared-memory slab; the persistent kernel reads them row by row
-  if (!attn_is_specialised(g) || variant == 4 || (bias != nullptr && variant == 3)) return attn_tcgen05_gen_fwd(qkv, scale, bias, o, lse, g, stream);
+  if (!attn_is_specialised(g) || variant == 4 || (bias != nullptr && variant >= 3)) return attn_tcgen05_gen_fwd(qkv, scale, bias, o, lse, g, stream);
+  if (variant == 5 && ((uintptr_t)qkv % 16 == 0)) return attn_tcgen05_fwd4(qkv, scale, bias, o, lse, g, stream);   // two items in flight per SM
   if (variant == 3 && ((uintptr_t)qkv % 16 == 0) && g.L * kRowPitch <= (96 / 32) * kCS64)
     return attn_tcgen05_fwd3(qkv, scale, bias, o, lse, g, stream);
   // the earlier generations do not produce the mean-cosine plane: define it as zero (= un-centred d(scale) in backward)
