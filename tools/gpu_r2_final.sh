@@ -10,4 +10,4 @@ timeout 900 python bench.py --workload config4 --batch-per-gpu 2 --no-cpu-baseli
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/r2_final_launches.csv python bench.py --profile-step --no-cpu-baseline --no-eager-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"; wc -l gpurun_out/r2_final_launches.csv
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attn_gen" -s 4 -c 4 -f -o gpurun_out/r2_attn_gen python tools/attn_gen_one.py > gpurun_out/ncu_attn_gen.log 2>&1; echo "ncu attn_gen exit $?"
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attn_tc_fwd3|attn_tc_bwd3|attn_rowdot3" -s 3 -c 3 -f -o gpurun_out/r2_final_attn python tools/attn_phases.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn exit $?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"attn_tc_fwd4|attn_tc_bwd3|attn_rowdot3" -s 3 -c 3 -f -o gpurun_out/r2_final_attn python tools/attn_phases.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn exit $?"
