@@ -73,3 +73,10 @@ def test_sharding_helpers():
     assert seen == list(range(16))
     m = torch.nn.Linear(2, 2)
     assert D.wrap_ddp(m) is m      # single process: no wrapping
+
+
+def test_numa_binding_never_raises():
+    """bind_to_gpu_numa_node is best effort: without NVML / a GPU it reports False instead of failing the launch."""
+    from swin_v2_weather_b200 import distributed as D
+    assert D.bind_to_gpu_numa_node(0) in (True, False)
+    assert D.bind_to_gpu_numa_node(99) is False

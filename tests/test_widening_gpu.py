@@ -111,3 +111,20 @@ def test_gelu_epilogue_tails():
     err = (gel.float() - want).abs()
     assert float(err[h.float() < -4].max()) < 3e-4          # exact value tends to 0-; ours is bounded by 4 * Phi(-4) + bf16 rounding of h
     assert float((err / want.abs().clamp_min(1.0)).max()) < 1e-2
+
+
+def test_copy_cropped_async_matches_a_plain_crop():
+    """Host -> device staging of the 721-row fields (loaders crop to 720 rows): one strided cudaMemcpy2DAsync
+    against the plain slice copy."""
+    from swin_v2_weather_b200.utils.host_io import copy_cropped_async
+    host = torch.randn(2, 5, 73, 64).pin_memory()
+    dst = torch.empty(2, 5, 72, 64, device=DEV)
+    s = torch.cuda.Stream(DEV)
+    with torch.cuda.stream(s):
+        copy_cropped_async(dst, host, s)
+    s.synchronize()
+    assert torch.equal(dst.cpu(), host[:, :, :72])
+    with pytest.raises(ValueError):
+        copy_cropped_async(dst, torch.randn(2, 5, 73, 64), s)          # not pinned
+    with pytest.raises(ValueError):
+        copy_cropped_async(dst, torch.randn(2, 5, 71, 64).pin_memory(), s)   # too few rows
