@@ -117,6 +117,7 @@ def test_copy_cropped_async_matches_a_plain_crop():
     """Host -> device staging of the 721-row fields (loaders crop to 720 rows): one strided cudaMemcpy2DAsync
     against the plain slice copy."""
     from swin_v2_weather_b200.utils.host_io import copy_cropped_async
+    DEV = torch.device("cuda", 0)
     host = torch.randn(2, 5, 73, 64).pin_memory()
     dst = torch.empty(2, 5, 72, 64, device=DEV)
     s = torch.cuda.Stream(DEV)
