@@ -18,8 +18,15 @@ def copy_cropped_async(dst: torch.Tensor, src: torch.Tensor, stream: torch.cuda.
     esz = dst.element_size()
     try:
         from cuda.bindings import runtime as cudart
-    except ImportError:                                     # older cuda-python layout
-        from cuda import cudart
+    except ImportError:
+        try:
+            from cuda import cudart                         # older cuda-python layout
+        except ImportError:                                 # no cuda-python: one contiguous copy per plane, same result
+            with torch.cuda.stream(stream):
+                for b in range(B):
+                    for c in range(C):
+                        dst[b, c].copy_(src[b, c, :rows], non_blocking=True)
+            return
     err, = cudart.cudaMemcpy2DAsync(dst.data_ptr(), rows * W * esz, src.data_ptr(), src.shape[2] * W * esz, rows * W * esz, B * C,
                                     cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, stream.cuda_stream)
     if int(err) != 0:
