@@ -17,6 +17,10 @@
 // Operand majors: K-major (row = m/n, 64 k per 128-byte row) or MN-major (row = k, 64 m/n per 128-byte row),
 // so nn.Linear forward (A k-major, B k-major), dgrad (B = weight read n-major) and wgrad (both operands
 // token-major, reduction over tokens, split-K with fp32 TMA reduce-add) all run without transposed copies.
+// Side work of the epilogue warps: (i) weight gradients -- the bias gradient (column sums of the m-major A operand) is taken
+// from the staged A tiles while the main loop runs (GemmTcParams::colsum_out, entry point swinb200_linear_wgrad);
+// (ii) BIAS_LN -- LayerNorm + DropPath scale + residual of every finished 128-row block (swinb200_linear_ln_residual; opt-in,
+// measured slower than the stand-alone LayerNorm kernel).
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
