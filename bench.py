@@ -249,10 +249,12 @@ def run_ours(args):
 
     zen_res = (torch.rand(B, 1, 720, 1440, generator=gen) * 2 - 1).to(dev) if config4 else None
 
-    def step(x, t):
+    def step(x, t, t_ready=None):
         for p in params:
             p.grad = None
         pred = ddp((x, zen_res, static)) if config4 else ddp(x)
+        if t_ready is not None:     # the target is only needed by the loss: its host -> device copy may still run under the forward
+            torch.cuda.current_stream().wait_event(t_ready)
         loss = lossf(pred, t, x)
         loss.backward()
         return loss
@@ -302,22 +304,29 @@ def run_ours(args):
     from swin_v2_weather_b200.utils.host_io import copy_cropped_async
     copy_stream = torch.cuda.Stream(dev)
     bufs = [(torch.empty(B, 73, 720, 1440, device=dev), torch.empty(B, 73, 720, 1440, device=dev)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
+    ready = [torch.cuda.Event(enable_timing=True) for _ in range(2)]        # the step's target has landed (its input landed before)
+    ready_x = [torch.cuda.Event() for _ in range(2)]                       # the step's input has landed
+    copy_begin = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     h2d_bytes = 2 * B * 73 * 720 * 1440 * 4
+    copy_ms = []          # duration of each step's host -> device copies, measured on the copy stream while the previous step runs
 
     def prefetch(i):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
+            copy_begin[slot].record(copy_stream)
             dx, dt = bufs[slot]
             # crop [:720]: each plane's first 720 rows are one contiguous 4.1 MB run -> one strided copy per tensor
             copy_cropped_async(dx, host_x, copy_stream)
+            ready_x[slot].record(copy_stream)
             copy_cropped_async(dt, host_t, copy_stream)
             ready[slot].record(copy_stream)
 
     loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    # blocking events: the host thread sleeps while it waits for the previous step's loss instead of spinning on a core that the
+    # other ranks' launch threads need (8 ranks share the node's CPUs)
+    loss_ready = [torch.cuda.Event(blocking=True) for _ in range(2)]
 
     def e2e_loop(n):
         # Per step: wait for the step's inputs (copied host -> device on the copy stream while the previous step ran),
@@ -330,16 +339,19 @@ def run_ours(args):
         last = None
         for i in range(n):
             slot = i % 2
+            if i >= 1 and ready[slot ^ 1].query():      # duration of step i-1's copies, before their events are recorded again
+                copy_ms.append(copy_begin[slot ^ 1].elapsed_time(ready[slot ^ 1]))
             if i + 1 < n:       # next step's copies first: they only wait for the step before this one and run under this step
                 prefetch(i + 1)
-            torch.cuda.current_stream().wait_event(ready[slot])
-            loss = step(*bufs[slot])
+            torch.cuda.current_stream().wait_event(ready_x[slot])
+            loss = step(*bufs[slot], t_ready=ready[slot])
             consumed[slot].record()
             loss_host[slot].copy_(loss.detach().reshape(()), non_blocking=True)
             loss_ready[slot].record()
             if i > 0:
                 loss_ready[slot ^ 1].synchronize()
                 last = float(loss_host[slot ^ 1])
+
         loss_ready[(n - 1) % 2].synchronize()
         last = float(loss_host[(n - 1) % 2])
         return last
@@ -477,7 +489,8 @@ def run_ours(args):
                    "attention_backend": "tcgen05" if ops_attn_is_tc(args.mode) else "cuda-core"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 4), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss, "numa_bound": bool(numa_bound)},
+                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": last_loss, "numa_bound": bool(numa_bound),
+                "h2d_copy_ms_per_step": round(statistics.median(copy_ms), 2) if copy_ms else None},
         "gpu_launches": launches,
         "roofline": roof,
         "kernel_families": families,
